@@ -1,0 +1,93 @@
+"""Seeded synthetic VOC-shaped inputs for the detection hot path.
+
+NumPy only, so the same arrays can feed the CUDA path, the oracle and the golden
+generator.  Seeds follow ``20260000 + config * 1000 + image_index``.
+"""
+import numpy as np
+
+SEED_BASE = 20260000
+
+
+def image_seed(config, image_index):
+    return SEED_BASE + config * 1000 + image_index
+
+
+def make_gt(seed, num_gt, num_classes=21):
+    """Ground truth of one image: boxes f32[G,4] (ymin,xmin,ymax,xmax) in [0,1], labels i64[G].
+
+    Centres U(0.1,0.9)^2, sides log-uniform in [0.05,0.6], corners clipped to [0,1],
+    minimum side 0.02 (what preprocessing hands to RONNet.bboxes_encode:
+    reference preprocessing/tf_image.py:416-419 clips GT to the crop)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    c = rng.uniform(0.1, 0.9, size=(num_gt, 2))
+    s = np.exp(rng.uniform(np.log(0.05), np.log(0.6), size=(num_gt, 2)))
+    lo = np.clip(c - s / 2, 0., 1.)
+    hi = np.clip(c + s / 2, 0., 1.)
+    hi = np.maximum(hi, lo + 0.02)
+    over = hi > 1.
+    lo = np.where(over, lo - (hi - 1.), lo)
+    hi = np.minimum(hi, 1.)
+    boxes = np.concatenate([lo, hi], 1).astype(np.float32)
+    labels = rng.integers(1, num_classes, size=num_gt).astype(np.int64)
+    return boxes, labels
+
+
+def make_gt_batch(config, batch, g_lo, g_hi, num_classes=21, g_max=None, first_image=0):
+    """Padded batch: boxes f32[B,Gmax,4], labels i64[B,Gmax], counts i32[B]."""
+    counts = np.zeros(batch, np.int32)
+    items = []
+    for b in range(batch):
+        seed = image_seed(config, first_image + b)
+        rng = np.random.Generator(np.random.PCG64(seed ^ 0x5bd1e995))
+        g = int(rng.integers(g_lo, g_hi + 1))
+        counts[b] = g
+        items.append(make_gt(seed, g, num_classes))
+    g_max = int(g_max or counts.max())
+    boxes = np.zeros((batch, g_max, 4), np.float32)
+    labels = np.zeros((batch, g_max), np.int64)
+    for b, (bx, lb) in enumerate(items):
+        boxes[b, :counts[b]] = bx
+        labels[b, :counts[b]] = lb
+    return boxes, labels, counts
+
+
+def make_predictions(seed, batch, num_anchors, num_classes=21, hot=300, dense=False):
+    """Network-output stand-ins for ``batch`` images.
+
+    loc f32[B,N,4] ~ N(0,0.5) clipped to [-3,3] (so exp stays finite); class scores
+    f32[B,N,C] = softmax of N(0,1) logits with +4 on background and +7 on one random
+    class for ``hot`` anchors per image; objectness f32[B,N] = sigmoid(N(-4,1.5)), 0.9 on
+    the hot anchors.  ``dense=True`` drops the background bias (top-k stress)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    B, N, C = batch, num_anchors, num_classes
+    loc = np.clip(rng.normal(0., 0.5, size=(B, N, 4)), -3., 3.).astype(np.float32)
+    logits = rng.normal(0., 1., size=(B, N, C)).astype(np.float32)
+    if not dense:
+        logits[:, :, 0] += np.float32(4.)
+    obj = rng.normal(-4., 1.5, size=(B, N)).astype(np.float32)
+    obj = (1. / (1. + np.exp(-obj.astype(np.float64)))).astype(np.float32)
+    hot = min(hot, N)
+    for b in range(B):
+        idx = rng.choice(N, size=hot, replace=False)
+        cls = rng.integers(1, C, size=hot)
+        logits[b, idx, cls] += np.float32(7.)
+        obj[b, idx] = np.float32(0.9)
+    m = logits.max(-1, keepdims=True)
+    e = np.exp((logits - m).astype(np.float32))
+    pred = (e / e.sum(-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    return loc, pred, obj
+
+
+def split_layers(x, layer_sizes, feat_shapes=None, anchors_per_cell=None):
+    """[B,N,...] -> list of per-layer [B,n_l,...] (or [B,H,W,A,...] when shapes are given),
+    the list-of-layers form the reference's net emits (nets/ron_vgg_320.py:486-508)."""
+    out = []
+    o = 0
+    for i, n in enumerate(layer_sizes):
+        t = np.ascontiguousarray(x[:, o:o + n])
+        if feat_shapes is not None:
+            H, W = feat_shapes[i]
+            t = t.reshape((x.shape[0], H, W, anchors_per_cell[i]) + x.shape[2:])
+        out.append(t)
+        o += n
+    return out

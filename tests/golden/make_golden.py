@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the reference's OWN,
+unmodified Python (/root/reference) over the NumPy emulation of TF-1 ops in
+oracle/tf1_shim.  Run in the build container only (the GPU box has no
+/root/reference); the .npz outputs are committed.
+
+    python tests/golden/make_golden.py
+
+What this pins: the reference's composition of ops (operand order, tie-breaking,
+thresholds, padding) for anchors, joint encode, decode, select/clip/min-size/sort,
+NMS ('min' and 'union'), TP/FP matching and AP.  Inputs come from
+ron_tensorflow_b200.synth (seeded) plus hand-made edge cases; every fixture stores
+the inputs it used, so tests never depend on generator stability.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('RON_REFERENCE', '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf1_shim'))
+sys.path.insert(1, REF)
+sys.path.insert(2, ROOT)
+
+import tensorflow as tf  # noqa: E402  (the shim)
+assert 'numpy-shim' in tf.__version__
+from nets import ron_vgg_320, ssd_vgg_512, ssd_vgg_300, ssd_common  # noqa: E402  (the reference)
+import tf_extended as tfe  # noqa: E402  (the reference)
+from ron_tensorflow_b200 import synth  # noqa: E402
+
+T = tf.convert_to_tensor
+
+
+def npy(x):
+    return x.a if isinstance(x, tf.Tensor) else np.asarray(x)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrs.items()})
+    print('%-28s %8.1f KB  %s' % (name, os.path.getsize(path) / 1024., sorted(arrs.keys())))
+
+
+# --------------------------------------------------------------------------- #
+# anchors
+# --------------------------------------------------------------------------- #
+def gen_anchors():
+    out = {}
+    for tag, net in (('ron320', ron_vgg_320.RONNet()), ('ssd512', ssd_vgg_512.SSDNet()),
+                     ('ssd300', ssd_vgg_300.SSDNet())):
+        anchors = net.anchors(net.params.img_shape)
+        for li, (y, x, h, w) in enumerate(anchors):
+            out['%s_L%d_y' % (tag, li)] = y
+            out['%s_L%d_x' % (tag, li)] = x
+            out['%s_L%d_h' % (tag, li)] = h
+            out['%s_L%d_w' % (tag, li)] = w
+    save('anchors', **out)
+
+
+# --------------------------------------------------------------------------- #
+# joint encode (RONNet.bboxes_encode -> ssd_common.tf_ssd_bboxes_encode)
+# --------------------------------------------------------------------------- #
+def run_encode(net, anchors, labels, boxes, pos, ign):
+    r = net.bboxes_encode(T(labels.astype(np.int64)), T(boxes.astype(np.float32)), anchors,
+                          positive_threshold=pos, ignore_threshold=ign)
+    lab = np.concatenate([npy(t).reshape(-1) for t in r[0]])
+    loc = np.concatenate([npy(t).reshape(-1, 4) for t in r[1]])
+    sco = np.concatenate([npy(t).reshape(-1) for t in r[2]])
+    box = np.concatenate([npy(t).reshape(-1, 4) for t in r[3]])
+    shapes = np.array([npy(t).shape[:3] for t in r[1]])
+    return lab, loc, sco, box, shapes
+
+
+def encode_cases():
+    cases = {}
+    # config 1: 5 synthetic GT boxes
+    b, l = synth.make_gt(synth.image_seed(1, 0), 5)
+    cases['cfg1_g5'] = (b, l, 0.5, 0.3)
+    # trainer thresholds (ron_net.py:278), many GT
+    b, l = synth.make_gt(synth.image_seed(2, 0), 50)
+    cases['cfg2_g50_t056'] = (b, l, 0.56, 0.3)
+    b, l = synth.make_gt(synth.image_seed(2, 1), 23)
+    cases['cfg2_g23'] = (b, l, 0.5, 0.3)
+    b, l = synth.make_gt(synth.image_seed(2, 2), 1)
+    cases['cfg2_g1'] = (b, l, 0.56, 0.3)
+    # grid-symmetric GT: exact float32 ties between anchors, two GT claiming one anchor,
+    # the notebook GT (notebooks/ssd_tests.ipynb cell 14), a whole-image box
+    b = np.array([[0.25, 0.25, 0.75, 0.75],
+                  [0.25, 0.25, 0.75, 0.75],
+                  [0.4, 0.4, 0.6, 0.6],
+                  [0.0, 0.0, 1.0, 1.0],
+                  [0.48, 0.136, 0.742, 0.552],
+                  [0.024, 0.0227, 0.996, 0.997],
+                  [0.1, 0.1, 0.2, 0.2],
+                  [0.8, 0.8, 0.9, 0.9]], np.float32)
+    l = np.array([3, 7, 12, 15, 12, 15, 1, 20], np.int64)
+    cases['ties'] = (b, l, 0.5, 0.3)
+    # all-zero overlap rows: a GT that only touches anchors outside the border mask and a
+    # zero-area GT -> both are force-matched to anchor 0 (lowest GT index wins)
+    b = np.array([[0.3, 0.3, 0.6, 0.7],
+                  [0.5, 0.5, 0.5, 0.5],
+                  [0.0, 0.0, 0.004, 0.004]], np.float32)
+    l = np.array([5, 9, 2], np.int64)
+    cases['zero_rows'] = (b, l, 0.5, 0.3)
+    return cases
+
+
+def gen_encode():
+    net = ron_vgg_320.RONNet()
+    anchors = net.anchors(net.params.img_shape)
+    out = {}
+    for name, (b, l, pos, ign) in encode_cases().items():
+        lab, loc, sco, box, shapes = run_encode(net, anchors, l, b, pos, ign)
+        out[name + '_in_boxes'] = b
+        out[name + '_in_labels'] = l
+        out[name + '_thr'] = np.array([pos, ign], np.float64)
+        out[name + '_labels'] = lab
+        out[name + '_loc'] = loc
+        out[name + '_scores'] = sco
+        out['anchor_boxes'] = box
+        out['layer_shapes'] = shapes
+    save('encode_ron320', **out)
+
+    # do_dual_max_match with its two never-used flags, on a small random overlap matrix
+    rng = np.random.Generator(np.random.PCG64(7))
+    ov = rng.uniform(0, 1, size=(6, 40)).astype(np.float32)
+    ov[ov < 0.35] = 0
+    ov[2] = 0
+    ov[:, 5] = ov[:, 6]
+    mm = {'ov': ov}
+    for ib in (True, False):
+        for gf in (True, False):
+            m, s = ssd_common.do_dual_max_match(T(ov), 0.5, 0.3, ignore_between=ib, gt_max_first=gf)
+            mm['m_%d%d' % (ib, gf)] = npy(m)
+            mm['s_%d%d' % (ib, gf)] = npy(s)
+    save('dual_max_match', **mm)
+
+
+# --------------------------------------------------------------------------- #
+# post-process (eval_ron_network.py:223-252)
+# --------------------------------------------------------------------------- #
+def gen_postprocess():
+    net = ron_vgg_320.RONNet()
+    p = net.params
+    anchors = net.anchors(p.img_shape)
+    layer_sizes = [a[0].shape[0] * a[0].shape[1] * a[2].shape[0] for a in anchors]
+    apc = [a[2].shape[0] for a in anchors]
+    N = sum(layer_sizes)
+    out = {}
+    for tag, seed, hot, dense, K, M, thr in (('a', 31, 300, False, 400, 200, 0.45),
+                                            ('dense', 32, 300, True, 200, 100, 0.4)):
+        loc, pred, obj = synth.make_predictions(seed, 1, N, p.num_classes, hot=hot, dense=dense)
+        loc_l = [T(t) for t in synth.split_layers(loc, layer_sizes, p.feat_shapes, apc)]
+        pred_l = [T(t) for t in synth.split_layers(pred, layer_sizes, p.feat_shapes, apc)]
+        obj_l = [T(t) for t in synth.split_layers(obj[..., None], layer_sizes, p.feat_shapes, apc)]
+        # eval_ron_network.py:226-236
+        dec = net.bboxes_decode(loc_l, anchors)
+        filt = [tf.cast(tf.greater(o, 0.03), tf.float32) * pr for o, pr in zip(obj_l, pred_l)]
+        rs, rb = net.detected_bboxes(filt, dec, select_threshold=0.01, nms_threshold=thr,
+                                     clipping_bbox=[0., 0., 1., 1.], top_k=K, keep_top_k=M)
+        classes = sorted(rs.keys())
+        out[tag + '_seed'] = np.array([seed, hot, int(dense), K, M], np.int64)
+        out[tag + '_nms_thr'] = np.array(thr, np.float64)
+        out[tag + '_in_loc'] = loc
+        out[tag + '_in_pred_sha'] = np.frombuffer(
+            __import__('hashlib').sha256(pred.tobytes()).digest(), np.uint8)
+        out[tag + '_in_obj_sha'] = np.frombuffer(
+            __import__('hashlib').sha256(obj.tobytes()).digest(), np.uint8)
+        out[tag + '_decoded'] = np.concatenate([npy(d).reshape(1, -1, 4) for d in dec], 1)
+        out[tag + '_scores'] = np.stack([npy(rs[c]) for c in classes], 1)      # [1,C-1,M]
+        out[tag + '_boxes'] = np.stack([npy(rb[c]) for c in classes], 1)       # [1,C-1,M,4]
+        # the stage before NMS, for stage-wise parity
+        s1, b1 = ssd_common.tf_ssd_bboxes_select(filt, dec, select_threshold=0.01,
+                                                 num_classes=p.num_classes)
+        b1 = tfe.bboxes_clip([0., 0., 1., 1.], b1)
+        s1, b1 = net.bboxes_filter_min(s1, b1, K)
+        s1, b1 = tfe.bboxes_sort(s1, b1, top_k=K)
+        out[tag + '_topk_scores'] = np.stack([npy(s1[c]) for c in classes], 1)
+        out[tag + '_topk_boxes'] = np.stack([npy(b1[c]) for c in classes], 1)
+        if tag == 'a':
+            # SSD order: select -> sort -> nms (ssd_vgg_512.py:182-201), no objectness
+            ssd = ssd_vgg_512.SSDNet()
+            rs2, rb2 = ssd.detected_bboxes(pred_l, dec, select_threshold=0.25,
+                                           nms_threshold=0.45, top_k=100, keep_top_k=50)
+            out['ssd_scores'] = np.stack([npy(rs2[c]) for c in classes], 1)
+            out['ssd_boxes'] = np.stack([npy(rb2[c]) for c in classes], 1)
+    save('postprocess_ron320', **out)
+
+
+def gen_nms():
+    rng = np.random.Generator(np.random.PCG64(11))
+    out = {}
+    K = 96
+    c = rng.uniform(0.2, 0.8, size=(K, 2))
+    s = rng.uniform(0.05, 0.4, size=(K, 2))
+    boxes = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+    scores = rng.uniform(0.02, 1, size=K).astype(np.float32)
+    scores[10] = scores[40]                     # equal scores: lower index first
+    scores[70:80] = 0                           # zero-padded slots are legal picks
+    boxes[70:80] = 0
+    boxes[20] = boxes[5]                        # duplicate box (overlap exactly 1)
+    boxes[33, 2] = boxes[33, 0]                 # zero-area real box
+    out['in_scores'] = scores
+    out['in_boxes'] = boxes
+    for mode in ('min', 'union'):
+        for thr, M in ((0.45, 200), (0.3, 20), (0.7, 64)):
+            rs, rb = tfe.bboxes_nms(T(scores), T(boxes), nms_threshold=thr, keep_top_k=M, mode=mode)
+            out['%s_%g_%d_scores' % (mode, thr, M)] = npy(rs)
+            out['%s_%g_%d_boxes' % (mode, thr, M)] = npy(rb)
+    rs, rb = tfe.bboxes_nms_batch(T(np.stack([scores, scores[::-1].copy()])),
+                                  T(np.stack([boxes, boxes[::-1].copy()])),
+                                  nms_threshold=0.45, keep_top_k=32)
+    out['batch_scores'] = npy(rs)
+    out['batch_boxes'] = npy(rb)
+    # bboxes_sort / bboxes_clip stand-alone
+    ss, sb = tfe.bboxes_sort(T(scores[None]), T(boxes[None]), top_k=50)
+    out['sort_scores'] = npy(ss)
+    out['sort_boxes'] = npy(sb)
+    wide = (boxes * 1.6 - 0.3).astype(np.float32)
+    out['clip_in'] = wide
+    out['clip_out'] = npy(tfe.bboxes_clip([0., 0., 1., 1.], T(wide)))
+    save('nms', **out)
+
+
+def gen_tpfp():
+    rng = np.random.Generator(np.random.PCG64(13))
+    B, M, Gm = 3, 24, 6
+    gboxes, glabels, counts = synth.make_gt_batch(9, B, 2, Gm, num_classes=4, g_max=Gm)
+    gdiff = (rng.uniform(size=(B, Gm)) < 0.25).astype(np.int64)
+    out = {'gboxes': gboxes, 'glabels': glabels, 'gdiff': gdiff}
+    d_s, d_b = {}, {}
+    for c in (1, 2, 3):
+        jit = rng.normal(0, 0.03, size=(B, M, 4)).astype(np.float32)
+        src = rng.integers(0, Gm, size=(B, M))
+        bx = np.take_along_axis(gboxes, src[..., None].repeat(4, -1), 1) + jit
+        sc = np.sort(rng.uniform(0, 1, size=(B, M)).astype(np.float32), -1)[:, ::-1].copy()
+        sc[:, -4:] = 0
+        bx[:, -4:] = 0
+        d_s[c], d_b[c] = sc, bx.astype(np.float32)
+        out['det_scores_%d' % c] = d_s[c]
+        out['det_boxes_%d' % c] = d_b[c]
+    n, tp, fp, _ = tfe.bboxes_matching_batch(d_s.keys(), {c: T(v) for c, v in d_s.items()},
+                                             {c: T(v) for c, v in d_b.items()},
+                                             T(glabels), T(gboxes), T(gdiff), matching_threshold=0.5)
+    for c in (1, 2, 3):
+        out['n_gt_%d' % c] = npy(n[c])
+        out['tp_%d' % c] = npy(tp[c])
+        out['fp_%d' % c] = npy(fp[c])
+        # metrics.py:169-175 filter, then precision_recall / AP (metrics.py:100-130,212-258)
+        s = d_s[c].reshape(-1)
+        t = npy(tp[c]).reshape(-1)
+        f = npy(fp[c]).reshape(-1)
+        mask = (t | f) & (s > np.float32(1e-4))
+        s, t, f = s[mask], t[mask], f[mask]
+        prec, rec = tfe.precision_recall(T(np.int64(npy(n[c]).sum())), s.shape[0], T(t), T(f), T(s))
+        out['prec_%d' % c] = npy(prec)
+        out['rec_%d' % c] = npy(rec)
+        out['ap07_%d' % c] = npy(tfe.average_precision_voc07(prec, rec))
+        out['ap12_%d' % c] = npy(tfe.average_precision_voc12(prec, rec))
+    save('tpfp', **out)
+
+
+if __name__ == '__main__':
+    gen_anchors()
+    gen_encode()
+    gen_postprocess()
+    gen_nms()
+    gen_tpfp()

@@ -1,0 +1,150 @@
+"""The oracle (oracle/ron_oracle.py) against the golden vectors recorded from the
+reference's own Python (tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import ron_oracle as O
+from ron_tensorflow_b200 import synth
+
+
+def eq(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(a, b, equal_nan=a.dtype.kind == 'f'), \
+        'mismatch at %s' % (np.argwhere(~((a == b) | ((a != a) & (b != b))))[:5],)
+
+
+@pytest.mark.parametrize('tag,spec', [('ron320', O.RON320), ('ssd512', O.SSD512), ('ssd300', O.SSD300)])
+def test_anchors_bit_exact(golden, tag, spec):
+    g = golden('anchors')
+    anchors = O.anchors_all_layers(spec)
+    for li, (y, x, h, w) in enumerate(anchors):
+        for nm, v in (('y', y), ('x', x), ('h', h), ('w', w)):
+            ref = g['%s_L%d_%s' % (tag, li, nm)]
+            assert ref.dtype == np.float32
+            eq(v, ref)
+    n = sum(a[0].shape[0] * a[0].shape[1] * a[2].shape[0] for a in anchors)
+    assert n == {'ron320': 21250, 'ssd512': 24564, 'ssd300': 8732}[tag]
+
+
+def _ron_tables():
+    anchors = O.anchors_all_layers(O.RON320)
+    return anchors, O.encode_anchor_tables(anchors, O.RON320.img_shape, O.RON320.allowed_borders)
+
+
+def test_encode_anchor_boxes_and_inside(golden):
+    g = golden('encode_ron320')
+    _, (enc, corners, inside) = _ron_tables()
+    eq(corners, g['anchor_boxes'])
+    assert int(inside.sum()) == 13743          # SURVEY.md measured fact
+
+
+@pytest.mark.parametrize('case', ['cfg1_g5', 'cfg2_g50_t056', 'cfg2_g23', 'cfg2_g1', 'ties', 'zero_rows'])
+def test_encode_bit_exact(golden, case):
+    g = golden('encode_ron320')
+    _, (enc, corners, inside) = _ron_tables()
+    pos, ign = g[case + '_thr']
+    r = O.encode_image(g[case + '_in_labels'], g[case + '_in_boxes'], enc, corners, inside,
+                       positive_threshold=pos, ignore_threshold=ign)
+    eq(r['labels'], g[case + '_labels'])
+    eq(r['scores'], g[case + '_scores'])
+    eq(r['loc'], g[case + '_loc'])          # same exp/log definition on both sides: bit-exact
+
+
+def test_generator_reproduces_golden_inputs(golden):
+    g = golden('encode_ron320')
+    b, l = synth.make_gt(synth.image_seed(1, 0), 5)
+    eq(b, g['cfg1_g5_in_boxes'])
+    eq(l, g['cfg1_g5_in_labels'])
+
+
+def test_dual_max_match_flags(golden):
+    g = golden('dual_max_match')
+    for ib in (1, 0):
+        for gf in (1, 0):
+            m, s = O.do_dual_max_match(g['ov'], 0.5, 0.3, bool(ib), bool(gf))
+            eq(m, g['m_%d%d' % (ib, gf)])
+            eq(s, g['s_%d%d' % (ib, gf)])
+
+
+def _post_inputs(g, tag):
+    seed, hot, dense, K, M = [int(v) for v in g[tag + '_seed']]
+    loc, pred, obj = synth.make_predictions(seed, 1, 21250, 21, hot=hot, dense=bool(dense))
+    if hashlib.sha256(pred.tobytes()).digest() != g[tag + '_in_pred_sha'].tobytes():
+        pytest.skip('numpy Generator stream differs from the one that made the fixture')
+    eq(loc, g[tag + '_in_loc'])
+    return loc, pred, obj, K, M
+
+
+@pytest.mark.parametrize('tag', ['a', 'dense'])
+def test_postprocess_bit_exact(golden, tag):
+    g = golden('postprocess_ron320')
+    loc, pred, obj, K, M = _post_inputs(g, tag)
+    dec_anchors = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+    eq(O.decode(loc[0], dec_anchors), g[tag + '_decoded'][0])
+    r = O.detected_bboxes_image(pred[0], loc[0], dec_anchors, objness=obj[0], objectness_threshold=0.03,
+                                select_threshold=0.01, nms_threshold=float(g[tag + '_nms_thr']),
+                                clipping_bbox=[0., 0., 1., 1.], top_k=K, keep_top_k=M)
+    eq(r['topk_scores'], g[tag + '_topk_scores'][0])
+    eq(r['topk_boxes'], g[tag + '_topk_boxes'][0])
+    eq(r['scores'], g[tag + '_scores'][0])
+    eq(r['boxes'], g[tag + '_boxes'][0])
+
+
+def test_postprocess_ssd_order(golden):
+    g = golden('postprocess_ron320')
+    loc, pred, obj, K, M = _post_inputs(g, 'a')
+    dec_anchors = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+    r = O.detected_bboxes_image(pred[0], loc[0], dec_anchors, select_threshold=0.25,
+                                nms_threshold=0.45, top_k=100, keep_top_k=50, min_size=None)
+    eq(r['scores'], g['ssd_scores'][0])
+    eq(r['boxes'], g['ssd_boxes'][0])
+
+
+@pytest.mark.parametrize('mode', ['min', 'union'])
+@pytest.mark.parametrize('thr,M', [(0.45, 200), (0.3, 20), (0.7, 64)])
+def test_nms_bit_exact(golden, mode, thr, M):
+    g = golden('nms')
+    s, b, ix = O.nms(g['in_scores'], g['in_boxes'], thr, M, mode)
+    eq(s, g['%s_%g_%d_scores' % (mode, thr, M)])
+    eq(b, g['%s_%g_%d_boxes' % (mode, thr, M)])
+    real = ix >= 0
+    eq(g['in_scores'][ix[real]], s[real])
+
+
+def test_nms_batch_sort_clip(golden):
+    g = golden('nms')
+    sc = np.stack([g['in_scores'], g['in_scores'][::-1]])
+    bx = np.stack([g['in_boxes'], g['in_boxes'][::-1]])
+    s, b, _ = O.nms_batch(sc, bx, 0.45, 32)
+    eq(s, g['batch_scores'])
+    eq(b, g['batch_boxes'])
+    o = O.topk_stable(g['in_scores'], 50)
+    eq(g['in_scores'][o][None], g['sort_scores'])
+    eq(g['in_boxes'][o][None], g['sort_boxes'])
+    eq(O.clip_boxes([0., 0., 1., 1.], g['clip_in']), g['clip_out'])
+
+
+def test_tpfp_and_ap(golden):
+    g = golden('tpfp')
+    B = g['glabels'].shape[0]
+    for c in (1, 2, 3):
+        n_all, tp_all, fp_all = [], [], []
+        for b in range(B):
+            n, tp, fp = O.bboxes_matching(c, g['det_scores_%d' % c][b], g['det_boxes_%d' % c][b],
+                                          g['glabels'][b], g['gboxes'][b], g['gdiff'][b])
+            n_all.append(n)
+            tp_all.append(tp)
+            fp_all.append(fp)
+        eq(np.array(n_all), g['n_gt_%d' % c])
+        eq(np.stack(tp_all), g['tp_%d' % c])
+        eq(np.stack(fp_all), g['fp_%d' % c])
+        prec, rec = O.precision_recall(sum(n_all), np.stack(tp_all).reshape(-1),
+                                       np.stack(fp_all).reshape(-1), g['det_scores_%d' % c].reshape(-1))
+        eq(prec, g['prec_%d' % c])
+        eq(rec, g['rec_%d' % c])
+        assert abs(O.average_precision_voc07(prec, rec) - float(g['ap07_%d' % c])) < 1e-12
+        assert abs(O.average_precision_voc12(prec, rec) - float(g['ap12_%d' % c])) < 1e-12
