@@ -1,0 +1,209 @@
+/*
+ * ronk.h -- C ABI of the B200-native detection hot path (libronk.so).
+ *
+ * Drop-in boundary for HiKapok/RON_Tensorflow's data-parallel hot path.  The
+ * reference has no FFI: its boundary is Python functions that build TF-1 graph
+ * nodes.  Each entry point below names the reference
+ * interface it replaces (file:line in the reference repo).  The reference-named
+ * Python modules in ron_tensorflow_b200/{nets,tf_extended} bind these through
+ * ctypes (ron_tensorflow_b200/_ffi.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the
+ *    name ends in _host; `stream` is a cudaStream_t passed as void* (NULL = default);
+ *  - every call is asynchronous on `stream`, never synchronises the device, allocates
+ *    nothing (scratch comes in through *_workspace_bytes + a caller buffer);
+ *  - return 0 on success, <0 = RONK_E*; ronk_last_error() gives a thread-local message;
+ *  - boxes are float32 (ymin, xmin, ymax, xmax); localisations are float32 (x, y, w, h);
+ *  - anchors are flattened layer-major, then (row, col, a) with a fastest (N total);
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef RONK_H_
+#define RONK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RONK_VERSION 100
+
+#define RONK_OK 0
+#define RONK_EINVAL (-1)   /* bad argument (NULL, size, alignment)            */
+#define RONK_ECUDA (-2)    /* CUDA runtime error (message has the CUDA text)  */
+#define RONK_ENOMEM (-3)   /* allocation failed (anchor handle only)          */
+#define RONK_ELIMIT (-4)   /* size outside what the kernels support           */
+
+#define RONK_KIND_RON 0    /* nets/ron_vgg_320.py:285-333 anchor rule */
+#define RONK_KIND_SSD 1    /* nets/ssd_vgg_512.py:286-338 anchor rule */
+
+#define RONK_NMS_MIN 0     /* overlap = inter / min(area_j, area_i)  tf_extended/bboxes.py:207-208 (default) */
+#define RONK_NMS_UNION 1   /* overlap = inter / ((area_j - inter) + area_i)  tf_extended/bboxes.py:205-206 */
+
+/* match flags: the two arguments of do_dual_max_match no caller changes (nets/ssd_common.py:49) */
+#define RONK_MATCH_DEFAULT 0
+#define RONK_MATCH_NO_IGNORE_BETWEEN 1   /* ignore_between=False */
+#define RONK_MATCH_NO_GT_MAX_FIRST 2     /* gt_max_first=False   */
+
+/* select flags */
+#define RONK_SELECT_DEFAULT 0
+#define RONK_SELECT_LOC_DECODED 1        /* loc_layers already hold decoded boxes (the reference's
+                                            detected_bboxes receives bboxes_decode's output) */
+
+typedef struct ronk_anchors ronk_anchors_t;
+
+int ronk_version(void);
+const char* ronk_last_error(void);
+
+/* ------------------------------------------------------------------ anchors
+ * Replaces RONNet.anchors -> ron_anchors_all_layers -> ron_anchor_one_layer
+ * (nets/ron_vgg_320.py:162-171,336-355,285-333), ssd_anchors_all_layers
+ * (nets/ssd_vgg_512.py:341-358, nets/ssd_vgg_300.py:361-380) and the anchor
+ * bookkeeping at the top of tf_ssd_bboxes_encode (nets/ssd_common.py:371-402).
+ * Runs the anchor-generator kernel once on the current device and keeps, in HBM:
+ *   table 0  decode anchors   float32[N,4] (y, x, h, w)       -- A.1, used by decode
+ *   table 1  encode anchors   float32[N,4] (cy, cx, h', w')   -- A.2, used by the encoding
+ *   table 2  anchor corners   float32[N,4] (ymin,xmin,ymax,xmax) second trip -- IoU, 4th encode output
+ *   table 3  inside mask      uint8[N]                        -- ssd_common.py:112-115
+ * sizes/ratios are ragged: layer l owns n_sizes[l] / n_ratios[l] consecutive doubles.
+ * allowed_borders == NULL means "every anchor is inside" (SSD nets have no borders).
+ */
+int ronk_anchors_create(int kind, int img_h, int img_w, int num_layers,
+                        const int* feat_shapes_host /*[L,2]*/,
+                        const double* sizes_host, const int* n_sizes_host /*[L]*/,
+                        const double* ratios_host, const int* n_ratios_host /*[L]*/,
+                        const double* steps_host /*[L]*/, double offset,
+                        const int* allowed_borders_host /*[L] or NULL*/,
+                        ronk_anchors_t** out);
+/* Arbitrary anchors, for callers of tf_ssd_bboxes_encode_layer / tf_ssd_bboxes_decode_layer
+ * (nets/ssd_common.py:77-147,448-474) that bring their own flattened (y, x, h, w) float32[N,4]:
+ * tables 0 and 1 are the given values, table 2 is one corner trip (ssd_common.py:105-108), the
+ * inside mask uses per-anchor borders (int32[N] or NULL = all inside).  One layer of shape (N,1,1). */
+int ronk_anchors_create_flat(int img_h, int img_w, int N, const float* yxhw_host,
+                             const int* allowed_border_host, ronk_anchors_t** out);
+void ronk_anchors_destroy(ronk_anchors_t* h);
+int ronk_anchors_num(const ronk_anchors_t* h);                 /* N */
+int ronk_anchors_num_layers(const ronk_anchors_t* h);          /* L */
+int ronk_anchors_layer_info(const ronk_anchors_t* h, int layer, int* H, int* W, int* A, int* offset);
+const void* ronk_anchors_table(const ronk_anchors_t* h, int which /*0..3*/); /* device pointer */
+/* per-layer h[A], w[A] exactly as the reference stores them (float32), host copy */
+int ronk_anchors_layer_hw(const ronk_anchors_t* h, int layer, float* h_host, float* w_host);
+
+/* ------------------------------------------------------------ match + encode
+ * Replaces RONNet.bboxes_encode -> tf_ssd_bboxes_encode -> tf_ssd_bboxes_encode_layer
+ * -> iou_matrix + do_dual_max_match (nets/ron_vgg_320.py:173-186,
+ * nets/ssd_common.py:337-414,77-147,27-75), batched over B images, plus the
+ * objectness-prior label of ron_losses (nets/ron_vgg_320.py:686,708).
+ * gt_boxes [B,Gmax,4], gt_labels int64 [B,Gmax], gt_counts int32 [B] (1 <= count <= Gmax).
+ * out_labels int64 [B,N] in {-1 ignore, 0 negative, class}; out_loc [B,N,4] (cx,cy,w,h);
+ * out_scores [B,N]; out_matched int32 [B,N] in {-2,-1,0..G-1} or NULL; out_objness int32 [B,N] or NULL.
+ * The workspace must be zeroed once (ronk_encode_workspace_init); every call leaves it zeroed.
+ */
+size_t ronk_encode_workspace_bytes(int B, int Gmax);
+int ronk_encode_workspace_init(void* ws, int B, int Gmax, void* stream);
+int ronk_match_encode(const ronk_anchors_t* h,
+                      const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_counts,
+                      int B, int Gmax, float positive_threshold, float ignore_threshold,
+                      const float* prior_scaling_host /*[4]*/, int match_flags,
+                      int64_t* out_labels, float* out_loc, float* out_scores,
+                      int32_t* out_matched, int32_t* out_objness,
+                      void* ws, void* stream);
+
+/* -------------------------------------------------------------------- decode
+ * Replaces RONNet.bboxes_decode -> tf_ssd_bboxes_decode(_layer)
+ * (nets/ron_vgg_320.py:188-195, nets/ssd_common.py:477-498,448-474).
+ * loc [B,n,4] for anchors [first_anchor, first_anchor+n) -> boxes [B,n,4].
+ */
+int ronk_decode(const ronk_anchors_t* h, const float* loc, int B, int first_anchor, int n,
+                const float* prior_scaling_host, float* out_boxes, void* stream);
+
+/* ------------------------------------------- decode + filter + select + top-k
+ * Replaces, fused and batched: bboxes_decode, the objectness gate of
+ * eval_ron_network.py:227-229, tf_ssd_bboxes_select(_layer) (nets/ssd_common.py:552-589,
+ * 504-549), tfe.bboxes_clip (tf_extended/bboxes.py:105-144), RONNet.bboxes_filter_min
+ * (nets/ron_vgg_320.py:196-233) and tfe.bboxes_sort (tf_extended/bboxes.py:60-101).
+ * Per-layer inputs exactly as the network emits them (no concatenation):
+ *   loc_layers[l]  float32 [B, n_l, 4]   cls_layers[l] float32 [B, n_l, C]
+ *   obj_layers[l]  float32 [B, n_l] or obj_layers == NULL (SSD / already gated)
+ * (the *_layers arrays are HOST arrays of L device pointers, 16-byte aligned).
+ * select_threshold >= 0 (None in the reference == 0).  clip_host == NULL: no clipping;
+ * min_size < 0: no min-size filter (SSD order: select -> sort).
+ * out_scores [B,C-1,K], out_boxes [B,C-1,K,4], out_idx int32 [B,C-1,K] (anchor index, -1 = padding) or NULL.
+ */
+size_t ronk_select_workspace_bytes(const ronk_anchors_t* h, int B, int C, int K);
+int ronk_decode_select_topk(const ronk_anchors_t* h,
+                            const float* const* loc_layers_host, const float* const* cls_layers_host,
+                            const float* const* obj_layers_host,
+                            int B, int C, float objectness_threshold, float select_threshold,
+                            const float* clip_host /*[4] or NULL*/, float min_size,
+                            const float* prior_scaling_host, int K, int select_flags,
+                            float* out_scores, float* out_boxes, int32_t* out_idx,
+                            void* ws, void* stream);
+
+/* ------------------------------------------------------- generic sort (top-k)
+ * Replaces tfe.bboxes_sort on arbitrary inputs (tf_extended/bboxes.py:60-101):
+ * per row, tf.nn.top_k(scores, K) (ties: lower index first) + gather + pad_axis.
+ * scores [S,N], boxes [S,N,4] -> out_scores [S,Kout], out_boxes [S,Kout,4], out_idx int32 or NULL,
+ * Kout = K (rows are zero-padded when N < K, tensors.py:59-86).
+ */
+int ronk_sort_topk(const float* scores, const float* boxes, int S, int N, int K,
+                   float* out_scores, float* out_boxes, int32_t* out_idx, void* stream);
+
+/* ----------------------------------------------------------------------- clip
+ * Replaces tfe.bboxes_clip (tf_extended/bboxes.py:105-144) on n boxes. */
+int ronk_clip(const float* clip_host /*[4]*/, const float* boxes, long long n, float* out_boxes, void* stream);
+
+/* ------------------------------------------------------------------------ NMS
+ * Replaces tfe.bboxes_nms_batch -> bboxes_nms (tf_extended/bboxes.py:262-302,173-234).
+ * scores [S,K], boxes [S,K,4]; rows are stably re-sorted by decreasing score unless
+ * assume_sorted != 0.  out_scores [S,M], out_boxes [S,M,4] zero padded;
+ * out_idx int32 [S,M] = position in the input row of each kept entry (-1 = padding) or NULL.
+ */
+size_t ronk_nms_workspace_bytes(int S, int K);
+int ronk_nms_batch(const float* scores, const float* boxes, int S, int K,
+                   float nms_threshold, int keep_top_k, int mode, int assume_sorted,
+                   float* out_scores, float* out_boxes, int32_t* out_idx,
+                   void* ws, void* stream);
+
+/* ---------------------------------------------------------------------- TP/FP
+ * Replaces tfe.bboxes_matching_batch -> bboxes_matching -> bboxes_jaccard
+ * (tf_extended/bboxes.py:407-450,316-404,527-554) for classes 1..C-1 at once.
+ * det_scores [B,C-1,M], det_boxes [B,C-1,M,4]; glabels int64 [B,Gmax], gboxes [B,Gmax,4],
+ * gdifficults int64 [B,Gmax] (zero padded like tf.train.batch(dynamic_pad=True)).
+ * out_n_gt int64 [B,C-1], out_tp / out_fp uint8 [B,C-1,M].
+ */
+int ronk_tpfp_match(const float* det_scores, const float* det_boxes, int B, int C, int M,
+                    const int64_t* glabels, const float* gboxes, const int64_t* gdifficults, int Gmax,
+                    float matching_threshold,
+                    int64_t* out_n_gt, uint8_t* out_tp, uint8_t* out_fp, void* stream);
+
+/* ------------------------------------------------- fine-grained functions
+ * One kernel per small reference function, so the whole Python surface is on the GPU:
+ * ronk_areas            areas                      nets/ssd_common.py:27-29     boxes [n,4] -> [n]
+ * ronk_pairwise         intersection / iou_matrix  nets/ssd_common.py:30-47     a [G,4], b [N,4] -> [G,N]
+ *                       (mode 0 = intersection, 1 = IoU with 0 where the union is 0)
+ * ronk_overlap_ref      bboxes_jaccard / bboxes_intersection  tf_extended/bboxes.py:527-583
+ *                       ref [1 or N,4] (device) vs boxes [N,4] -> [N] (mode 0 = jaccard, 1 = intersection)
+ * ronk_select_mask      tf_ssd_bboxes_select_layer nets/ssd_common.py:504-549   pred [B,n,C], boxes [B,n,4]
+ *                       -> scores [B,C',n], boxes [B,C',n,4] zeroed where score <= thr (C' skips ignore_class)
+ * ronk_dual_max_match   do_dual_max_match          nets/ssd_common.py:49-75     overlap [G,N] -> matched int64 [N], scores [N]
+ */
+int ronk_areas(const float* boxes, int n, float* out, void* stream);
+int ronk_pairwise(const float* a, int G, const float* b, int N, int mode, float* out, void* stream);
+int ronk_overlap_ref(const float* ref, int ref_n, const float* boxes, int N, int mode, float* out, void* stream);
+int ronk_select_mask(const float* pred, const float* boxes, int B, int n, int C, float select_threshold,
+                     int ignore_class, float* out_scores, float* out_boxes, void* stream);
+size_t ronk_dual_max_match_workspace_bytes(int G);
+int ronk_dual_max_match(const float* overlap, int G, int N, float high_thres, float low_thres, int match_flags,
+                        int64_t* out_matched, float* out_scores, void* ws, void* stream);
+
+/* number of kernel launches issued by this library in this process since load
+ * (bench.py reports it as gpu_launches) */
+long long ronk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RONK_H_ */

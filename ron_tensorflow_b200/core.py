@@ -1,0 +1,435 @@
+"""Torch glue over the C ABI: device memory, streams, workspaces.  PyTorch is plumbing
+here (allocator + stream + torch.distributed); every computation is a libronk kernel.
+
+All functions take/return CUDA tensors; NumPy inputs are uploaded.  Nothing in this module
+(or anywhere in the package) falls back to a CPU implementation.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+_PS = (0.1, 0.1, 0.2, 0.2)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('ron_tensorflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def as_cuda(x, dtype, device=None):
+    """torch CUDA tensor of ``dtype``, contiguous; uploads NumPy / CPU tensors."""
+    _require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    if not t.is_cuda:
+        t = t.to(device or 'cuda', non_blocking=True)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class _DevView(object):
+    """Zero-copy torch view of device memory owned by an anchor handle."""
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), True),
+                                         'version': 2}
+        self._owner = owner
+
+
+class AnchorSet(object):
+    """Anchor handle (ronk_anchors_t): runs the anchor-generator kernel once and keeps the
+    decode / encode / corner / inside tables resident in HBM."""
+
+    def __init__(self, kind, img_shape, feat_shapes, anchor_sizes, anchor_ratios, anchor_steps,
+                 anchor_offset=0.5, allowed_borders=None, device=None):
+        _require_cuda()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else
+                                   torch.device(device).index or 0)
+        L = len(feat_shapes)
+        if not (len(anchor_sizes) == len(anchor_ratios) == len(anchor_steps) == L):
+            raise ValueError('feat_shapes, anchor_sizes, anchor_ratios and anchor_steps must have one entry per layer')
+        if allowed_borders is not None and len(allowed_borders) != L:
+            raise ValueError('allowed_borders must have one entry per layer')
+        sizes = [float(s) for ls in anchor_sizes for s in (ls if isinstance(ls, (list, tuple)) else [ls])]
+        n_sizes = [len(ls) if isinstance(ls, (list, tuple)) else 1 for ls in anchor_sizes]
+        ratios = [float(r) for lr in anchor_ratios for r in lr]
+        n_ratios = [len(lr) for lr in anchor_ratios]
+        fs = [int(v) for s in feat_shapes for v in s]
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _ffi.lib().ronk_anchors_create(
+                _ffi.KIND_RON if kind == 'ron' else _ffi.KIND_SSD, int(img_shape[0]), int(img_shape[1]), L,
+                _ffi.iarr(fs), _ffi.darr(sizes), _ffi.iarr(n_sizes), _ffi.darr(ratios), _ffi.iarr(n_ratios),
+                _ffi.darr(anchor_steps), float(anchor_offset),
+                _ffi.iarr(allowed_borders) if allowed_borders is not None else None, ctypes.byref(h))
+        _ffi.check(rc)
+        self.gen_params = (kind, tuple(img_shape), [tuple(s) for s in feat_shapes], anchor_sizes, anchor_ratios,
+                           list(anchor_steps), anchor_offset)
+        self.allowed_borders = None if allowed_borders is None else [int(b) for b in allowed_borders]
+        self._finish(h, kind, img_shape)
+
+    @classmethod
+    def flat(cls, img_shape, yxhw, allowed_border=None, device=None):
+        """Arbitrary flattened anchors (ronk_anchors_create_flat): yxhw float32 [N,4] on the host,
+        allowed_border int [N] or None."""
+        _require_cuda()
+        self = cls.__new__(cls)
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else
+                                   torch.device(device).index or 0)
+        a = np.ascontiguousarray(np.asarray(yxhw, np.float32).reshape(-1, 4))
+        b = None if allowed_border is None else np.ascontiguousarray(np.asarray(allowed_border, np.int32).reshape(-1))
+        if b is not None and b.shape[0] != a.shape[0]:
+            raise ValueError('allowed_border must have one entry per anchor')
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _ffi.lib().ronk_anchors_create_flat(
+                int(img_shape[0]), int(img_shape[1]), int(a.shape[0]),
+                a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                b.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if b is not None else None, ctypes.byref(h))
+        _ffi.check(rc)
+        self.gen_params = None
+        self.allowed_borders = None
+        self._finish(h, 'flat', img_shape)
+        return self
+
+    def with_borders(self, allowed_borders):
+        """Same generated anchors, another per-layer border list (None = all inside)."""
+        ab = None if allowed_borders is None else [int(b) for b in allowed_borders]
+        if ab == self.allowed_borders or self.gen_params is None:
+            return self
+        cache = self.__dict__.setdefault('_border_variants', {})
+        key = None if ab is None else tuple(ab)
+        if key not in cache:
+            kind, img_shape, fs, sizes, ratios, steps, off = self.gen_params
+            cache[key] = AnchorSet(kind, img_shape, fs, sizes, ratios, steps, off, ab, self.device)
+        return cache[key]
+
+    def _finish(self, h, kind, img_shape):
+        self._h = h
+        self.kind = kind
+        self.img_shape = tuple(img_shape)
+        self.N = _ffi.lib().ronk_anchors_num(h)
+        L = self.L = _ffi.lib().ronk_anchors_num_layers(h)
+        self.layers = []          # (H, W, A, offset)
+        for l in range(L):
+            H, W, A, o = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            _ffi.check(_ffi.lib().ronk_anchors_layer_info(h, l, ctypes.byref(H), ctypes.byref(W),
+                                                          ctypes.byref(A), ctypes.byref(o)))
+            self.layers.append((H.value, W.value, A.value, o.value))
+        self.layer_sizes = [H * W * A for H, W, A, _ in self.layers]
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            try:
+                _ffi.lib().ronk_anchors_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def table(self, which):
+        """0: decode anchors [N,4] (y,x,h,w); 1: encode anchors [N,4] (cy,cx,h',w');
+        2: anchor corners [N,4]; 3: inside mask uint8 [N].  Zero-copy CUDA tensors."""
+        ptr = _ffi.lib().ronk_anchors_table(self._h, which)
+        if which == 3:
+            v = _DevView(ptr, (self.N,), '|u1', self)
+        else:
+            v = _DevView(ptr, (self.N, 4), '<f4', self)
+        return torch.as_tensor(v, device=self.device)
+
+    def layer_hw(self, l):
+        A = self.layers[l][2]
+        hh, ww = (ctypes.c_float * A)(), (ctypes.c_float * A)()
+        _ffi.check(_ffi.lib().ronk_anchors_layer_hw(self._h, l, hh, ww))
+        return np.array(hh, np.float32), np.array(ww, np.float32)
+
+    def as_reference_list(self):
+        """[(y[H,W,1], x[H,W,1], h[A], w[A])] float32 NumPy, the structure RONNet.anchors returns
+        in the reference (nets/ron_vgg_320.py:336-355); the grids come from the kernel's table."""
+        dec = self.table(0).cpu().numpy()
+        out = []
+        for l, (H, W, A, o) in enumerate(self.layers):
+            t = dec[o:o + H * W * A].reshape(H, W, A, 4)
+            hh, ww = self.layer_hw(l)
+            out.append((np.ascontiguousarray(t[:, :, 0:1, 0]), np.ascontiguousarray(t[:, :, 0:1, 1]), hh, ww))
+        return out
+
+
+# workspaces are cached per (device, stream, shape): the encode workspace must stay zeroed
+# between calls (the kernels restore it), torch.zeros provides the initial state.
+_ws_cache = {}
+
+
+def _workspace(kind, nbytes, zero, device):
+    key = (kind, device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
+    t = _ws_cache.get(key)
+    if t is None:
+        n = (int(nbytes) + 7) // 8
+        t = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=torch.int64, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def match_encode(anchors, gt_boxes, gt_labels, gt_counts, positive_threshold=0.5, ignore_threshold=0.3,
+                 prior_scaling=_PS, ignore_between=True, gt_max_first=True, want_matched=False,
+                 want_objness=False, out=None):
+    """Batched joint matching + encoding (ronk_match_encode).  gt_boxes [B,Gmax,4] f32,
+    gt_labels [B,Gmax] i64, gt_counts [B] i32.  Returns dict(labels [B,N] i64, loc [B,N,4],
+    scores [B,N], matched [B,N] i32?, objness [B,N] i32?)."""
+    dev = anchors.device
+    gb = as_cuda(gt_boxes, torch.float32, dev)
+    gl = as_cuda(gt_labels, torch.int64, dev)
+    gc = as_cuda(gt_counts, torch.int32, dev)
+    if gb.dim() != 3 or gb.shape[-1] != 4 or gl.shape != gb.shape[:2] or gc.shape != gb.shape[:1]:
+        raise ValueError('expected gt_boxes [B,Gmax,4], gt_labels [B,Gmax], gt_counts [B]')
+    B, G = int(gb.shape[0]), int(gb.shape[1])
+    if B < 1 or G < 1:
+        raise ValueError('need at least one image and one ground-truth slot')
+    N = anchors.N
+    o = out or {}
+    labels = o.get('labels') if o.get('labels') is not None else torch.empty((B, N), dtype=torch.int64, device=dev)
+    loc = o.get('loc') if o.get('loc') is not None else torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    scores = o.get('scores') if o.get('scores') is not None else torch.empty((B, N), dtype=torch.float32, device=dev)
+    matched = torch.empty((B, N), dtype=torch.int32, device=dev) if want_matched else None
+    objn = torch.empty((B, N), dtype=torch.int32, device=dev) if want_objness else None
+    L = _ffi.lib()
+    ws = _workspace('enc', L.ronk_encode_workspace_bytes(B, G), True, dev)
+    flags = (0 if ignore_between else _ffi.MATCH_NO_IGNORE_BETWEEN) | (0 if gt_max_first else _ffi.MATCH_NO_GT_MAX_FIRST)
+    with torch.cuda.device(dev):
+        rc = L.ronk_match_encode(anchors.handle, _ptr(gb), _ptr(gl), _ptr(gc), B, G, float(positive_threshold),
+                                 float(ignore_threshold), _ffi.farr(prior_scaling), flags, _ptr(labels), _ptr(loc),
+                                 _ptr(scores), _ptr(matched), _ptr(objn), _ptr(ws), _stream())
+    _ffi.check(rc)
+    r = dict(labels=labels, loc=loc, scores=scores)
+    if want_matched:
+        r['matched'] = matched
+    if want_objness:
+        r['objness'] = objn
+    return r
+
+
+def decode(anchors, loc, first_anchor=0, prior_scaling=_PS):
+    """loc [B,n,4] (or [n,4]) for anchors [first_anchor, first_anchor+n) -> boxes, same shape."""
+    dev = anchors.device
+    t = as_cuda(loc, torch.float32, dev)
+    shp = t.shape
+    t3 = t.reshape(-1, shp[-2], 4) if t.dim() >= 2 else None
+    if t3 is None or shp[-1] != 4:
+        raise ValueError('loc must be [..., n, 4]')
+    out = torch.empty_like(t3)
+    with torch.cuda.device(dev):
+        rc = _ffi.lib().ronk_decode(anchors.handle, _ptr(t3), int(t3.shape[0]), int(first_anchor), int(t3.shape[1]),
+                                    _ffi.farr(prior_scaling), _ptr(out), _stream())
+    _ffi.check(rc)
+    return out.reshape(shp)
+
+
+def _layer_ptrs(anchors, tensors, last, what):
+    """list of per-layer tensors [B, ..., last] -> (contiguous tensors, ctypes array of pointers, B)."""
+    if len(tensors) != anchors.L:
+        raise ValueError('%s: expected %d layers, got %d' % (what, anchors.L, len(tensors)))
+    ts, B = [], None
+    for l, x in enumerate(tensors):
+        t = as_cuda(x, torch.float32, anchors.device)
+        n_l = anchors.layer_sizes[l]
+        b = int(t.shape[0])
+        if t.numel() != b * n_l * last:
+            raise ValueError('%s layer %d: expected [B,%d,%d] elements, got shape %s' % (what, l, n_l, last, tuple(t.shape)))
+        B = b if B is None else B
+        if b != B:
+            raise ValueError('%s: inconsistent batch size' % what)
+        ts.append(t)
+    arr = (ctypes.c_void_p * anchors.L)(*[t.data_ptr() for t in ts])
+    return ts, arr, B
+
+
+def decode_select_topk(anchors, loc_layers, cls_layers, obj_layers=None, objectness_threshold=0.0,
+                       select_threshold=None, clip=None, min_size=None, top_k=400, prior_scaling=_PS,
+                       loc_is_decoded=False, want_idx=False):
+    """Fused decode + objectness gate + select + clip + min-size + per-class top-k
+    (ronk_decode_select_topk).  Returns scores [B,C-1,K], boxes [B,C-1,K,4], idx [B,C-1,K] or None."""
+    dev = anchors.device
+    loc_t, loc_p, B = _layer_ptrs(anchors, loc_layers, 4, 'localisations')
+    C = int(as_cuda(cls_layers[0], torch.float32, dev).shape[-1])
+    cls_t, cls_p, B2 = _layer_ptrs(anchors, cls_layers, C, 'predictions')
+    if B2 != B:
+        raise ValueError('predictions and localisations disagree on the batch size')
+    obj_t, obj_p = None, None
+    if obj_layers is not None:
+        obj_t, obj_p, B3 = _layer_ptrs(anchors, obj_layers, 1, 'objectness')
+        if B3 != B:
+            raise ValueError('objectness and predictions disagree on the batch size')
+    K = int(top_k)
+    sel = 0.0 if select_threshold is None else float(select_threshold)
+    scores = torch.empty((B, C - 1, K), dtype=torch.float32, device=dev)
+    boxes = torch.empty((B, C - 1, K, 4), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, C - 1, K), dtype=torch.int32, device=dev) if want_idx else None
+    L = _ffi.lib()
+    ws = _workspace('sel', max(L.ronk_select_workspace_bytes(anchors.handle, B, C, K), 256), False, dev)
+    with torch.cuda.device(dev):
+        rc = L.ronk_decode_select_topk(
+            anchors.handle, loc_p, cls_p, obj_p, B, C, float(objectness_threshold), sel,
+            _ffi.farr(clip) if clip is not None else None, -1.0 if min_size is None else float(min_size),
+            _ffi.farr(prior_scaling), K, _ffi.SELECT_LOC_DECODED if loc_is_decoded else 0,
+            _ptr(scores), _ptr(boxes), _ptr(idx), _ptr(ws), _stream())
+    _ffi.check(rc)
+    del loc_t, cls_t, obj_t
+    return scores, boxes, idx
+
+
+def sort_topk(scores, boxes, top_k, want_idx=False):
+    """tfe.bboxes_sort on [S,N] / [S,N,4] rows (ronk_sort_topk)."""
+    s = as_cuda(scores, torch.float32)
+    b = as_cuda(boxes, torch.float32, s.device)
+    if s.dim() != 2 or b.shape != s.shape + (4,):
+        raise ValueError('expected scores [S,N] and boxes [S,N,4]')
+    S, N = int(s.shape[0]), int(s.shape[1])
+    K = int(top_k)
+    if K > N:
+        # tf.nn.top_k(k > N) is an InvalidArgumentError in the reference (bboxes.py:86)
+        raise ValueError('input must have at least k columns')
+    os_ = torch.empty((S, K), dtype=torch.float32, device=s.device)
+    ob = torch.empty((S, K, 4), dtype=torch.float32, device=s.device)
+    oi = torch.empty((S, K), dtype=torch.int32, device=s.device) if want_idx else None
+    with torch.cuda.device(s.device):
+        rc = _ffi.lib().ronk_sort_topk(_ptr(s), _ptr(b), S, N, K, _ptr(os_), _ptr(ob), _ptr(oi), _stream())
+    _ffi.check(rc)
+    return os_, ob, oi
+
+
+def clip(bbox_ref, boxes):
+    b = as_cuda(boxes, torch.float32)
+    if b.shape[-1] != 4:
+        raise ValueError('boxes must be [..., 4]')
+    ref = [float(v) for v in (bbox_ref.tolist() if hasattr(bbox_ref, 'tolist') else bbox_ref)]
+    out = torch.empty_like(b)
+    with torch.cuda.device(b.device):
+        rc = _ffi.lib().ronk_clip(_ffi.farr(ref), _ptr(b), b.numel() // 4, _ptr(out), _stream())
+    _ffi.check(rc)
+    return out
+
+
+def nms_batch(scores, boxes, nms_threshold=0.5, keep_top_k=200, mode='min', assume_sorted=False, want_idx=False):
+    """tfe.bboxes_nms_batch on [S,K] / [S,K,4] rows (ronk_nms_batch)."""
+    if mode not in ('min', 'union'):
+        raise ValueError('unknown mode to use for nms.')
+    s = as_cuda(scores, torch.float32)
+    b = as_cuda(boxes, torch.float32, s.device)
+    if s.dim() != 2 or b.shape != s.shape + (4,):
+        raise ValueError('expected scores [S,K] and boxes [S,K,4]')
+    S, K = int(s.shape[0]), int(s.shape[1])
+    M = int(keep_top_k)
+    os_ = torch.empty((S, M), dtype=torch.float32, device=s.device)
+    ob = torch.empty((S, M, 4), dtype=torch.float32, device=s.device)
+    oi = torch.empty((S, M), dtype=torch.int32, device=s.device) if want_idx else None
+    L = _ffi.lib()
+    ws = None if assume_sorted else _workspace('nms', L.ronk_nms_workspace_bytes(S, K), False, s.device)
+    with torch.cuda.device(s.device):
+        rc = L.ronk_nms_batch(_ptr(s), _ptr(b), S, K, float(nms_threshold), M,
+                              _ffi.NMS_MIN if mode == 'min' else _ffi.NMS_UNION, 1 if assume_sorted else 0,
+                              _ptr(os_), _ptr(ob), _ptr(oi), _ptr(ws), _stream())
+    _ffi.check(rc)
+    return os_, ob, oi
+
+
+def tpfp_match(det_scores, det_boxes, glabels, gboxes, gdifficults, matching_threshold=0.5):
+    """tfe.bboxes_matching_batch for classes 1..C-1 at once.  det_scores [B,C-1,M],
+    det_boxes [B,C-1,M,4]; returns n_gt int64 [B,C-1], tp / fp bool [B,C-1,M]."""
+    s = as_cuda(det_scores, torch.float32)
+    b = as_cuda(det_boxes, torch.float32, s.device)
+    gl = as_cuda(glabels, torch.int64, s.device)
+    gb = as_cuda(gboxes, torch.float32, s.device)
+    gd = as_cuda(gdifficults, torch.int64, s.device)
+    if s.dim() != 3 or b.shape != s.shape + (4,) or gb.shape != gl.shape + (4,) or gd.shape != gl.shape \
+            or gl.shape[0] != s.shape[0]:
+        raise ValueError('expected det [B,C-1,M](,4) and ground truth [B,Gmax](,4)')
+    B, CM, M = (int(v) for v in s.shape)
+    G = int(gl.shape[1])
+    n_gt = torch.empty((B, CM), dtype=torch.int64, device=s.device)
+    tp = torch.empty((B, CM, M), dtype=torch.uint8, device=s.device)
+    fp = torch.empty((B, CM, M), dtype=torch.uint8, device=s.device)
+    with torch.cuda.device(s.device):
+        rc = _ffi.lib().ronk_tpfp_match(_ptr(s), _ptr(b), B, CM + 1, M, _ptr(gl), _ptr(gb), _ptr(gd), G,
+                                        float(matching_threshold), _ptr(n_gt), _ptr(tp), _ptr(fp), _stream())
+    _ffi.check(rc)
+    return n_gt, tp.bool(), fp.bool()
+
+
+def launch_count():
+    return int(_ffi.lib().ronk_launch_count())
+
+
+# ----------------------------------------------------------------------------- fine-grained functions
+def pairwise(a, b, what):
+    """areas / intersection / iou_matrix of nets/ssd_common.py:27-47."""
+    L = _ffi.lib()
+    a = a.reshape(-1, 4).contiguous()
+    if what == 'areas':
+        out = torch.empty((a.shape[0], 1), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _ffi.check(L.ronk_areas(_ptr(a), int(a.shape[0]), _ptr(out), _stream()))
+        return out
+    b = b.reshape(-1, 4).contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _ffi.check(L.ronk_pairwise(_ptr(a), int(a.shape[0]), _ptr(b), int(b.shape[0]), 1 if what == 'iou' else 0,
+                                   _ptr(out), _stream()))
+    return out
+
+
+def dual_max_match(overlap, high, low, ignore_between=True, gt_max_first=True):
+    if overlap.dim() != 2 or overlap.shape[0] < 1 or overlap.shape[1] < 1:
+        raise ValueError('overlap_matrix must be [num_gt >= 1, num_anchors >= 1]')
+    G, N = int(overlap.shape[0]), int(overlap.shape[1])
+    matched = torch.empty((N,), dtype=torch.int64, device=overlap.device)
+    scores = torch.empty((N,), dtype=torch.float32, device=overlap.device)
+    L = _ffi.lib()
+    ws = _workspace('dmm', L.ronk_dual_max_match_workspace_bytes(G), False, overlap.device)
+    flags = (0 if ignore_between else _ffi.MATCH_NO_IGNORE_BETWEEN) | (0 if gt_max_first else _ffi.MATCH_NO_GT_MAX_FIRST)
+    with torch.cuda.device(overlap.device):
+        _ffi.check(L.ronk_dual_max_match(_ptr(overlap), G, N, float(high), float(low), flags, _ptr(matched),
+                                         _ptr(scores), _ptr(ws), _stream()))
+    return matched, scores
+
+
+def select_mask(pred, boxes, select_threshold=None, ignore_class=0):
+    """pred [B,n,C], boxes [B,n,4] -> scores [B,C',n], boxes [B,C',n,4] (ssd_common.py:537-547)."""
+    B, n, C = (int(v) for v in pred.shape)
+    CM = C - 1 if 0 <= ignore_class < C else C
+    thr = 0.0 if select_threshold is None else float(select_threshold)
+    os_ = torch.empty((B, CM, n), dtype=torch.float32, device=pred.device)
+    ob = torch.empty((B, CM, n, 4), dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        _ffi.check(_ffi.lib().ronk_select_mask(_ptr(pred), _ptr(boxes), B, n, C, thr, int(ignore_class), _ptr(os_),
+                                               _ptr(ob), _stream()))
+    return os_, ob
+
+
+def overlap_ref(bbox_ref, boxes, what):
+    """bboxes_jaccard / bboxes_intersection of tf_extended/bboxes.py:527-583."""
+    b = as_cuda(boxes, torch.float32).reshape(-1, 4)
+    r = as_cuda(bbox_ref, torch.float32, b.device).reshape(-1, 4)
+    if r.shape[0] not in (1, b.shape[0]):
+        raise ValueError('bbox_ref must be (4,) or (N, 4)')
+    out = torch.empty((b.shape[0],), dtype=torch.float32, device=b.device)
+    with torch.cuda.device(b.device):
+        _ffi.check(_ffi.lib().ronk_overlap_ref(_ptr(r), int(r.shape[0]), _ptr(b), int(b.shape[0]),
+                                               0 if what == 'jaccard' else 1, _ptr(out), _stream()))
+    return out

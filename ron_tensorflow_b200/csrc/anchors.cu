@@ -1,0 +1,277 @@
+// Anchor handle + anchor-generator kernel (K0).
+// Reference: nets/ron_vgg_320.py:285-355 (RON rule), nets/ssd_vgg_512.py:286-358 (SSD rule),
+// nets/ssd_common.py:371-402 (re-derived encode anchors, per-anchor borders) and :103-115
+// (second-trip corners, inside mask).  SURVEY.md Appendix A.1-A.3.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ronk {
+
+struct AnchorGenParams {
+    LayerTable tab;
+    float step[kMaxLayers];
+    float lo_y[kMaxLayers], lo_x[kMaxLayers], hi_y[kMaxLayers], hi_x[kMaxLayers];
+    float h[kMaxShapes], w[kMaxShapes];
+    float img_h, img_w, offset;
+    int has_border;
+};
+
+// One thread per anchor.  The centre grid is three float32 ops in the reference's order
+// ((i + offset) * step) / img; per-shape h, w arrive already rounded to float32 (the
+// reference evaluates them in Python double and stores to a float32 array).
+__global__ void __launch_bounds__(256)
+anchor_gen_kernel(const __grid_constant__ AnchorGenParams p, float4* __restrict__ dec,
+                  float4* __restrict__ enc, float4* __restrict__ cor, uint8_t* __restrict__ inside) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.tab.N) return;
+    int l = layer_of(p.tab, n);
+    int local = n - p.tab.offs[l];
+    int A = p.tab.A[l];
+    int a = local % A;
+    int cell = local / A;
+    int j = cell % p.tab.W[l];
+    int i = cell / p.tab.W[l];
+    float y = (((float)i + p.offset) * p.step[l]) / p.img_h;
+    float x = (((float)j + p.offset) * p.step[l]) / p.img_w;
+    float h = p.h[p.tab.hw_off[l] + a];
+    float w = p.w[p.tab.hw_off[l] + a];
+    dec[n] = make_float4(y, x, h, w);
+    // first trip: corners from the original anchors (ssd_common.py:375-378)
+    float ymin_ = y - h / 2.f, xmin_ = x - w / 2.f, ymax_ = y + h / 2.f, xmax_ = x + w / 2.f;
+    // re-derived centre/size (ssd_common.py:381)
+    float cy = (ymin_ + ymax_) / 2.f, cx = (xmin_ + xmax_) / 2.f;
+    float hh = ymax_ - ymin_, ww = xmax_ - xmin_;
+    enc[n] = make_float4(cy, cx, hh, ww);
+    // second trip (ssd_common.py:105-108)
+    float ymin = cy - hh / 2.f, xmin = cx - ww / 2.f, ymax = cy + hh / 2.f, xmax = cx + ww / 2.f;
+    cor[n] = make_float4(ymin, xmin, ymax, xmax);
+    bool in = true;
+    if (p.has_border)
+        in = (ymin >= p.lo_y[l]) && (xmin >= p.lo_x[l]) && (ymax < p.hi_y[l]) && (xmax < p.hi_x[l]);
+    inside[n] = in ? 1 : 0;
+}
+
+// Arbitrary flattened anchors: corners + inside mask from given (y, x, h, w) and per-anchor borders.
+__global__ void __launch_bounds__(256)
+anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ border, int N, int img_h, int img_w,
+                   float4* __restrict__ cor, uint8_t* __restrict__ inside) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float4 a = yxhw[n];
+    float ymin = a.x - a.z / 2.f, xmin = a.y - a.w / 2.f, ymax = a.x + a.z / 2.f, xmax = a.y + a.w / 2.f;
+    cor[n] = make_float4(ymin, xmin, ymax, xmax);
+    bool in = true;
+    if (border) {
+        double b = (double)border[n];
+        float lo_y = (float)(-b * 1. / img_h), lo_x = (float)(-b * 1. / img_w);
+        float hi_y = (float)((img_h + b) * 1. / img_h), hi_x = (float)((img_w + b) * 1. / img_w);
+        in = (ymin >= lo_y) && (xmin >= lo_x) && (ymax < hi_y) && (xmax < hi_x);
+    }
+    inside[n] = in ? 1 : 0;
+}
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" int ronk_anchors_create_flat(int img_h, int img_w, int N, const float* yxhw, const int* border,
+                                        ronk_anchors_t** out) {
+    RONK_REQUIRE(out != nullptr, RONK_EINVAL, "ronk_anchors_create_flat: out is NULL");
+    *out = nullptr;
+    RONK_REQUIRE(yxhw && N >= 1 && N <= (1 << 24) && img_h > 0 && img_w > 0, RONK_EINVAL,
+                 "ronk_anchors_create_flat: bad argument");
+    ronk_anchors* h = new (std::nothrow) ronk_anchors();
+    RONK_REQUIRE(h != nullptr, RONK_ENOMEM, "ronk_anchors_create_flat: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->kind = -1;
+    h->img_h = img_h;
+    h->img_w = img_w;
+    h->tab.L = 1;
+    h->tab.N = N;
+    h->tab.offs[0] = 0;
+    h->tab.offs[1] = N;
+    h->tab.H[0] = N;
+    h->tab.W[0] = 1;
+    h->tab.A[0] = 1;
+    int* d_border = nullptr;
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_dec, (size_t)N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_enc, (size_t)N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cor, (size_t)N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_inside, (size_t)N);
+    if (e == cudaSuccess && border) e = cudaMalloc(&d_border, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_dec, yxhw, (size_t)N * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_enc, yxhw, (size_t)N * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && border) e = cudaMemcpy(d_border, border, (size_t)N * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        anchor_flat_kernel<<<(N + 255) / 256, 256>>>((const float4*)h->d_enc, d_border, N, img_h, img_w,
+                                                     (float4*)h->d_cor, h->d_inside);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (d_border) cudaFree(d_border);
+    if (e != cudaSuccess) {
+        int r = cuda_fail(e, "ronk_anchors_create_flat");
+        ronk_anchors_destroy(h);
+        return (e == cudaErrorMemoryAllocation) ? RONK_ENOMEM : r;
+    }
+    *out = h;
+    return RONK_OK;
+}
+
+extern "C" int ronk_anchors_create(int kind, int img_h, int img_w, int num_layers,
+                                   const int* feat_shapes, const double* sizes, const int* n_sizes,
+                                   const double* ratios, const int* n_ratios, const double* steps,
+                                   double offset, const int* borders, ronk_anchors_t** out) {
+    RONK_REQUIRE(out != nullptr, RONK_EINVAL, "ronk_anchors_create: out is NULL");
+    *out = nullptr;
+    RONK_REQUIRE(kind == RONK_KIND_RON || kind == RONK_KIND_SSD, RONK_EINVAL, "ronk_anchors_create: unknown kind");
+    RONK_REQUIRE(num_layers >= 1 && num_layers <= kMaxLayers, RONK_ELIMIT, "ronk_anchors_create: 1..16 layers supported");
+    RONK_REQUIRE(img_h > 0 && img_w > 0, RONK_EINVAL, "ronk_anchors_create: bad image shape");
+    RONK_REQUIRE(feat_shapes && sizes && n_sizes && ratios && n_ratios && steps, RONK_EINVAL,
+                 "ronk_anchors_create: NULL parameter array");
+
+    ronk_anchors* h = new (std::nothrow) ronk_anchors();
+    RONK_REQUIRE(h != nullptr, RONK_ENOMEM, "ronk_anchors_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    AnchorGenParams* p = new (std::nothrow) AnchorGenParams();
+    if (!p) { delete h; set_error("ronk_anchors_create: out of host memory"); return RONK_ENOMEM; }
+    memset(p, 0, sizeof(*p));
+    h->kind = kind;
+    h->img_h = img_h;
+    h->img_w = img_w;
+    LayerTable& t = h->tab;
+    t.L = num_layers;
+    int n = 0, shapes = 0, so = 0, ro = 0;
+    int rc = RONK_OK;
+    for (int l = 0; l < num_layers && rc == RONK_OK; ++l) {
+        int S = n_sizes[l], R = n_ratios[l];
+        int A = (kind == RONK_KIND_RON) ? S * R : S + R;
+        if (S < 1 || R < 0 || A < 1 || shapes + A > kMaxShapes || (kind == RONK_KIND_SSD && S > 2)) {
+            set_error("ronk_anchors_create: unsupported sizes/ratios for a layer");
+            rc = RONK_ELIMIT;
+            break;
+        }
+        t.offs[l] = n;
+        t.H[l] = feat_shapes[2 * l];
+        t.W[l] = feat_shapes[2 * l + 1];
+        t.A[l] = A;
+        t.hw_off[l] = shapes;
+        if (t.H[l] < 1 || t.W[l] < 1) { set_error("ronk_anchors_create: bad feature shape"); rc = RONK_EINVAL; break; }
+        const double* sz = sizes + so;
+        const double* rt = ratios + ro;
+        float* hh = h->h_host + shapes;
+        float* ww = h->w_host + shapes;
+        if (kind == RONK_KIND_RON) {
+            // a = ratio_index * S + size_index; h = s / img_h / sqrt(r), w = s / img_w * sqrt(r) in double
+            for (int i = 0; i < R; ++i)
+                for (int j = 0; j < S; ++j) {
+                    hh[i * S + j] = (float)(sz[j] / (double)img_h / sqrt(rt[i]));
+                    ww[i * S + j] = (float)(sz[j] / (double)img_w * sqrt(rt[i]));
+                }
+        } else {
+            hh[0] = (float)(sz[0] / (double)img_h);
+            ww[0] = (float)(sz[0] / (double)img_w);
+            int di = 1;
+            if (S > 1) {
+                hh[1] = (float)(sqrt(sz[0] * sz[1]) / (double)img_h);
+                ww[1] = (float)(sqrt(sz[0] * sz[1]) / (double)img_w);
+                di = 2;
+            }
+            for (int i = 0; i < R; ++i) {
+                hh[i + di] = (float)(sz[0] / (double)img_h / sqrt(rt[i]));
+                ww[i + di] = (float)(sz[0] / (double)img_w * sqrt(rt[i]));
+            }
+        }
+        p->step[l] = (float)steps[l];
+        if (borders) {
+            double b = (double)borders[l];
+            p->lo_y[l] = (float)(-b * 1. / img_h);
+            p->lo_x[l] = (float)(-b * 1. / img_w);
+            p->hi_y[l] = (float)((img_h + b) * 1. / img_h);
+            p->hi_x[l] = (float)((img_w + b) * 1. / img_w);
+        }
+        long long nl = (long long)t.H[l] * t.W[l] * A;
+        if (n + nl > (1 << 24)) { set_error("ronk_anchors_create: more than 2^24 anchors"); rc = RONK_ELIMIT; break; }
+        n += (int)nl;
+        shapes += A;
+        so += S;
+        ro += R;
+    }
+    if (rc != RONK_OK) { delete p; delete h; return rc; }
+    t.offs[num_layers] = n;
+    t.N = n;
+    p->tab = t;
+    memcpy(p->h, h->h_host, sizeof(p->h));
+    memcpy(p->w, h->w_host, sizeof(p->w));
+    p->img_h = (float)img_h;
+    p->img_w = (float)img_w;
+    p->offset = (float)offset;
+    p->has_border = borders ? 1 : 0;
+
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_dec, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_enc, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cor, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_inside, (size_t)n);
+    if (e == cudaSuccess) {
+        anchor_gen_kernel<<<(n + 255) / 256, 256>>>(*p, (float4*)h->d_dec, (float4*)h->d_enc,
+                                                    (float4*)h->d_cor, h->d_inside);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // creation only; compute calls never sync
+    delete p;
+    if (e != cudaSuccess) {
+        int r = cuda_fail(e, "ronk_anchors_create");
+        ronk_anchors_destroy(h);
+        return (e == cudaErrorMemoryAllocation) ? RONK_ENOMEM : r;
+    }
+    *out = h;
+    return RONK_OK;
+}
+
+extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
+    if (!h) return;
+    if (h->d_dec) cudaFree(h->d_dec);
+    if (h->d_enc) cudaFree(h->d_enc);
+    if (h->d_cor) cudaFree(h->d_cor);
+    if (h->d_inside) cudaFree(h->d_inside);
+    delete h;
+}
+
+extern "C" int ronk_anchors_num(const ronk_anchors_t* h) { return h ? h->tab.N : RONK_EINVAL; }
+extern "C" int ronk_anchors_num_layers(const ronk_anchors_t* h) { return h ? h->tab.L : RONK_EINVAL; }
+
+extern "C" int ronk_anchors_layer_info(const ronk_anchors_t* h, int layer, int* H, int* W, int* A, int* offset) {
+    RONK_REQUIRE(h && layer >= 0 && layer < h->tab.L, RONK_EINVAL, "ronk_anchors_layer_info: bad handle or layer");
+    if (H) *H = h->tab.H[layer];
+    if (W) *W = h->tab.W[layer];
+    if (A) *A = h->tab.A[layer];
+    if (offset) *offset = h->tab.offs[layer];
+    return RONK_OK;
+}
+
+extern "C" const void* ronk_anchors_table(const ronk_anchors_t* h, int which) {
+    if (!h) return nullptr;
+    switch (which) {
+        case 0: return h->d_dec;
+        case 1: return h->d_enc;
+        case 2: return h->d_cor;
+        case 3: return h->d_inside;
+    }
+    return nullptr;
+}
+
+extern "C" int ronk_anchors_layer_hw(const ronk_anchors_t* h, int layer, float* hh, float* ww) {
+    RONK_REQUIRE(h && layer >= 0 && layer < h->tab.L && hh && ww, RONK_EINVAL, "ronk_anchors_layer_hw: bad argument");
+    int A = h->tab.A[layer], o = h->tab.hw_off[layer];
+    memcpy(hh, h->h_host + o, sizeof(float) * A);
+    memcpy(ww, h->w_host + o, sizeof(float) * A);
+    return RONK_OK;
+}

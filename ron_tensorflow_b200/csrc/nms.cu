@@ -1,0 +1,187 @@
+// K3: batched greedy NMS, one warp per (image, class) segment.
+//
+// Reference: tf_extended/bboxes.py:173-234 (bboxes_nms) and :262-302 (bboxes_nms_batch).
+// Spec: SURVEY.md Appendix A.7.  Bit-exact (kept set and order) against oracle/ron_oracle.py.
+//
+// The reference's loop "pick the first live box, kill everything it overlaps, stop after M
+// picks" is equivalent to: walk the score-sorted candidates once and keep a candidate iff no
+// previously KEPT box suppresses it and fewer than M are kept.  The warp walks the candidates
+// in chunks of 32 (one per lane): every lane tests its candidate against the kept list in
+// shared memory (broadcast reads), a 32x32 suppression bit-matrix is built inside the chunk,
+// and the chunk is resolved with ballots/shuffles.  Memory is O(M) per segment for any K, the
+// walk stops as soon as M boxes are kept.  overlap = inter / min(area_j, area_i) ('min',
+// the reference default) or inter / ((area_j - inter) + area_i) ('union'), safe_divide
+// (0 when the denominator is <= 0), keep test is strict: overlap < threshold.
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace ronk {
+
+constexpr int kNmsWarps = 4;
+
+struct NmsParams {
+    const float* scores;
+    const float4* boxes;
+    const int* order;   // [S,K] sorted positions, or NULL when rows are already sorted
+    int S, K, M, mode;
+    float thr;
+    float* out_scores;
+    float4* out_boxes;
+    int* out_idx;
+};
+
+// does kept box i suppress candidate j?  (j is the later one: tf_extended/bboxes.py:195-211)
+__device__ __forceinline__ bool suppresses(float4 bj, float vj, float4 bi, float vi, int mode, float thr,
+                                           bool zero_suppresses) {
+    float h = fminf(bj.z, bi.z) - fmaxf(bj.x, bi.x);
+    float w = fminf(bj.w, bi.w) - fmaxf(bj.y, bi.y);
+    if (h > 0.f && w > 0.f) {
+        float inner = h * w;
+        float den = (mode == RONK_NMS_UNION) ? ((vj - inner) + vi) : fminf(vj, vi);
+        float o = (den > 0.f) ? inner / den : 0.f;
+        return !(o < thr);
+    }
+    return zero_suppresses;   // overlap is exactly 0: suppressed only when !(0 < thr)
+}
+
+__global__ void __launch_bounds__(kNmsWarps * 32)
+nms_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = blockIdx.x * kNmsWarps + warp;
+    if (seg >= p.S) return;
+    const int per_warp = ((p.M + 32) * 20 + 15) & ~15;   // float4 + float for M kept and 32 chunk entries
+    unsigned char* base = smem + (size_t)warp * per_warp;
+    float4* s_kbox = reinterpret_cast<float4*>(base);
+    float4* s_cbox = s_kbox + p.M;
+    float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
+    float* s_cvol = s_kvol + p.M;
+
+    const bool zero_supp = !(0.f < p.thr);
+    const size_t in0 = (size_t)seg * p.K, out0 = (size_t)seg * p.M;
+    int count = 0;
+    for (int c0 = 0; c0 < p.K && count < p.M; c0 += 32) {
+        const int j = c0 + lane;
+        const bool valid = j < p.K;
+        int pos = -1;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        if (valid) {
+            pos = p.order ? p.order[in0 + j] : j;
+            box = p.boxes[in0 + pos];
+            score = p.scores[in0 + pos];
+        }
+        const float vol = (box.w - box.y) * (box.z - box.x);
+        bool alive = valid;
+        for (int i = 0; i < count; ++i) {
+            float4 kb = s_kbox[i];
+            float kv = s_kvol[i];
+            if (alive && suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp)) alive = false;
+        }
+        s_cbox[lane] = box;
+        s_cvol[lane] = vol;
+        __syncwarp();
+        unsigned supp = 0u;   // earlier lanes of this chunk that would suppress this lane if kept
+        for (int i = 0; i < 31; ++i) {
+            float4 kb = s_cbox[i];
+            float kv = s_cvol[i];
+            if (i < lane && suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp)) supp |= 1u << i;
+        }
+        const unsigned alive_mask = __ballot_sync(full, alive);
+        unsigned kept = 0u;
+        int room = p.M - count;
+        for (int l = 0; l < 32; ++l) {
+            unsigned sl = __shfl_sync(full, supp, l);
+            if (((alive_mask >> l) & 1u) && !(sl & kept) && room > 0) {
+                kept |= 1u << l;
+                --room;
+            }
+        }
+        if ((kept >> lane) & 1u) {
+            int r = count + __popc(kept & ((1u << lane) - 1u));
+            s_kbox[r] = box;
+            s_kvol[r] = vol;
+            p.out_scores[out0 + r] = score;
+            p.out_boxes[out0 + r] = box;
+            if (p.out_idx) p.out_idx[out0 + r] = pos;
+        }
+        count += __popc(kept);
+        __syncwarp();
+    }
+    for (int r = count + lane; r < p.M; r += 32) {   // pad_axis (tensors.py:59-86)
+        p.out_scores[out0 + r] = 0.f;
+        p.out_boxes[out0 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.out_idx) p.out_idx[out0 + r] = -1;
+    }
+}
+
+// stable descending order of every row (tf.nn.top_k(k = row length), bboxes.py:179-180)
+struct RowSrc {
+    const float* g;
+    __device__ __forceinline__ u64 get(int i) const {
+        unsigned u = __float_as_uint(g[i]);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        return ((u64)u << 32) | (u64)(0xffffffffu - (unsigned)i);
+    }
+};
+
+__global__ void __launch_bounds__(kTopkThreads)
+row_order_kernel(const float* __restrict__ scores, int K, int* __restrict__ order) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    u64* s_sort = reinterpret_cast<u64*>(smem);
+    __shared__ unsigned s_hist[256];
+    __shared__ int s_ctl[4];
+    const size_t row = blockIdx.x;
+    RowSrc src{scores + row * K};
+    block_topk_sorted(src, K, K, s_hist, s_ctl, s_sort);
+    for (int r = threadIdx.x; r < K; r += kTopkThreads)
+        order[row * K + r] = (int)(0xffffffffu - (unsigned)(s_sort[r] & 0xffffffffull));
+}
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" size_t ronk_nms_workspace_bytes(int S, int K) {
+    if (S < 1 || K < 1) return 0;
+    return (size_t)S * K * sizeof(int);
+}
+
+extern "C" int ronk_nms_batch(const float* scores, const float* boxes, int S, int K, float nms_threshold,
+                              int keep_top_k, int mode, int assume_sorted, float* out_scores, float* out_boxes,
+                              int32_t* out_idx, void* ws, void* stream) {
+    RONK_REQUIRE(scores && boxes && out_scores && out_boxes, RONK_EINVAL, "ronk_nms_batch: NULL argument");
+    RONK_REQUIRE(S >= 1 && K >= 1 && keep_top_k >= 1, RONK_EINVAL, "ronk_nms_batch: S, K, keep_top_k must be >= 1");
+    RONK_REQUIRE(mode == RONK_NMS_MIN || mode == RONK_NMS_UNION, RONK_EINVAL, "unknown mode to use for nms.");
+    RONK_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)out_boxes % 16) == 0, RONK_EINVAL,
+                 "ronk_nms_batch: box pointers must be 16-byte aligned");
+    RONK_REQUIRE(assume_sorted || ws, RONK_EINVAL, "ronk_nms_batch: workspace required unless assume_sorted");
+    RONK_REQUIRE(assume_sorted || K <= 16384, RONK_ELIMIT, "ronk_nms_batch: unsorted rows support K <= 16384");
+    RONK_REQUIRE(keep_top_k <= 2048, RONK_ELIMIT, "ronk_nms_batch: keep_top_k <= 2048");
+    cudaStream_t st = (cudaStream_t)stream;
+    NmsParams p;
+    p.scores = scores;
+    p.boxes = (const float4*)boxes;
+    p.order = nullptr;
+    p.S = S; p.K = K; p.M = keep_top_k; p.mode = mode; p.thr = nms_threshold;
+    p.out_scores = out_scores;
+    p.out_boxes = (float4*)out_boxes;
+    p.out_idx = out_idx;
+    if (!assume_sorted) {
+        int P = 1;
+        while (P < K) P <<= 1;
+        size_t smem = (size_t)P * sizeof(u64);
+        if (smem > 48 * 1024)
+            RONK_CUDA(cudaFuncSetAttribute(row_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        row_order_kernel<<<S, kTopkThreads, smem, st>>>(scores, K, (int*)ws);
+        RONK_LAUNCHED();
+        p.order = (const int*)ws;
+    }
+    size_t smem = (size_t)kNmsWarps * ((((size_t)keep_top_k + 32) * 20 + 15) & ~(size_t)15);
+    if (smem > 48 * 1024)
+        RONK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_kernel<<<(S + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, smem, st>>>(p);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}

@@ -1,0 +1,131 @@
+// TP/FP matching of detections against ground truth, one warp per (image, class).
+//
+// Reference: tf_extended/bboxes.py:316-404 (bboxes_matching), :407-450 (bboxes_matching_batch),
+// :527-554 (bboxes_jaccard).  Spec: SURVEY.md Appendix A.8.  Bit-exact against the oracle.
+// The detection loop is inherently sequential (a GT can be matched once); lanes run over the
+// ground-truth boxes of the image, staged once per CTA in shared memory.
+#include "common.cuh"
+
+namespace ronk {
+
+constexpr int kTpfpWarps = 8;
+
+struct TpfpParams {
+    const float* det_scores;
+    const float4* det_boxes;
+    int B, C, M, Gmax;
+    const long long* glabels;
+    const float4* gboxes;
+    const long long* gdiff;
+    float thr;
+    long long* out_n_gt;
+    uint8_t* out_tp;
+    uint8_t* out_fp;
+};
+
+__global__ void __launch_bounds__(kTpfpWarps * 32)
+tpfp_kernel(const __grid_constant__ TpfpParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* s_gbox = reinterpret_cast<float4*>(smem);                 // [Gmax]
+    float* s_garea = reinterpret_cast<float*>(s_gbox + p.Gmax);       // [Gmax]
+    int* s_glab = reinterpret_cast<int*>(s_garea + p.Gmax);           // [Gmax]
+    int* s_gdiff = s_glab + p.Gmax;                                   // [Gmax]
+    unsigned* s_match = reinterpret_cast<unsigned*>(s_gdiff + p.Gmax);   // [warps][ceil(Gmax/32)]
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int CM = p.C - 1;
+    const int words = (p.Gmax + 31) / 32;
+    for (int g = threadIdx.x; g < p.Gmax; g += blockDim.x) {
+        float4 gb = p.gboxes[(size_t)b * p.Gmax + g];
+        s_gbox[g] = gb;
+        s_garea[g] = (gb.z - gb.x) * (gb.w - gb.y);
+        long long l = p.glabels[(size_t)b * p.Gmax + g];
+        s_glab[g] = (l < -2147483647ll || l > 2147483647ll) ? -2147483647 : (int)l;
+        s_gdiff[g] = p.gdiff[(size_t)b * p.Gmax + g] != 0;
+    }
+    for (int i = threadIdx.x; i < kTpfpWarps * words; i += blockDim.x) s_match[i] = 0u;
+    __syncthreads();
+    const int ci = blockIdx.x * kTpfpWarps + warp;   // class index 0..C-2
+    if (ci >= CM) return;
+    const int label = ci + 1;
+    unsigned* match = s_match + warp * words;
+
+    // n_gbboxes = #(glabel == c and not difficult)   (bboxes.py:344-345)
+    int cnt = 0;
+    for (int g = lane; g < p.Gmax; g += 32) cnt += (s_glab[g] == label && !s_gdiff[g]) ? 1 : 0;
+    cnt = __reduce_add_sync(full, cnt);
+    const size_t seg = (size_t)b * CM + ci;
+    if (lane == 0) p.out_n_gt[seg] = cnt;
+
+    for (int i = 0; i < p.M; ++i) {
+        const float4 r = p.det_boxes[seg * p.M + i];
+        const float rarea = (r.z - r.x) * (r.w - r.y);
+        // jaccard vs every GT, masked by class; lane-local first argmax
+        float best = -1.f;
+        int bestg = 0x7fffffff;
+        for (int g = lane; g < p.Gmax; g += 32) {
+            float4 gb = s_gbox[g];
+            float h = fmaxf(fminf(gb.z, r.z) - fmaxf(gb.x, r.x), 0.f);
+            float w = fmaxf(fminf(gb.w, r.w) - fmaxf(gb.y, r.y), 0.f);
+            float inter = h * w;
+            float uni = (-inter + s_garea[g]) + rarea;
+            float jac = (uni > 0.f) ? inter / uni : 0.f;
+            jac = jac * ((s_glab[g] == label) ? 1.f : 0.f);
+            if (jac > best) { best = jac; bestg = g; }
+        }
+        // warp argmax, first occurrence: jaccard >= 0 so the bit pattern orders like the value
+        unsigned bits = (bestg == 0x7fffffff) ? 0u : __float_as_uint(best) + 1u;   // +1: lanes with no GT lose
+        unsigned m = __reduce_max_sync(full, bits);
+        unsigned cand = (bits == m && bestg != 0x7fffffff) ? (unsigned)bestg : 0xffffffffu;
+        const int idx = (int)__reduce_min_sync(full, cand);
+        const float jmax = __uint_as_float(m - 1u);
+        const bool is_match = jmax > p.thr;
+        const bool existing = (match[idx >> 5] >> (idx & 31)) & 1u;
+        const bool nd = !s_gdiff[idx];
+        const bool tp = nd && is_match && !existing;
+        const bool fp = nd && (existing || !is_match);
+        __syncwarp();
+        if (lane == 0) {
+            p.out_tp[seg * p.M + i] = tp ? 1 : 0;
+            p.out_fp[seg * p.M + i] = fp ? 1 : 0;
+            if (nd && is_match) match[idx >> 5] |= 1u << (idx & 31);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" int ronk_tpfp_match(const float* det_scores, const float* det_boxes, int B, int C, int M,
+                               const int64_t* glabels, const float* gboxes, const int64_t* gdifficults, int Gmax,
+                               float matching_threshold, int64_t* out_n_gt, uint8_t* out_tp, uint8_t* out_fp,
+                               void* stream) {
+    RONK_REQUIRE(det_boxes && glabels && gboxes && gdifficults && out_n_gt && out_tp && out_fp, RONK_EINVAL,
+                 "ronk_tpfp_match: NULL argument");
+    RONK_REQUIRE(B >= 1 && C >= 2 && M >= 1 && Gmax >= 1, RONK_EINVAL, "ronk_tpfp_match: bad sizes");
+    RONK_REQUIRE(B <= 65535, RONK_ELIMIT, "ronk_tpfp_match: B <= 65535 per call");
+    RONK_REQUIRE(((uintptr_t)det_boxes % 16) == 0 && ((uintptr_t)gboxes % 16) == 0, RONK_EINVAL,
+                 "ronk_tpfp_match: box pointers must be 16-byte aligned");
+    size_t smem = (size_t)Gmax * (16 + 4 + 4 + 4) + (size_t)kTpfpWarps * ((Gmax + 31) / 32) * 4;
+    RONK_REQUIRE(smem <= 200 * 1024, RONK_ELIMIT, "ronk_tpfp_match: Gmax too large");
+    if (smem > 48 * 1024)
+        RONK_CUDA(cudaFuncSetAttribute(tpfp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TpfpParams p;
+    p.det_scores = det_scores;
+    p.det_boxes = (const float4*)det_boxes;
+    p.B = B; p.C = C; p.M = M; p.Gmax = Gmax;
+    p.glabels = (const long long*)glabels;
+    p.gboxes = (const float4*)gboxes;
+    p.gdiff = (const long long*)gdifficults;
+    p.thr = matching_threshold;
+    p.out_n_gt = (long long*)out_n_gt;
+    p.out_tp = out_tp;
+    p.out_fp = out_fp;
+    dim3 grid((C - 1 + kTpfpWarps - 1) / kTpfpWarps, B);
+    tpfp_kernel<<<grid, kTpfpWarps * 32, smem, (cudaStream_t)stream>>>(p);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}

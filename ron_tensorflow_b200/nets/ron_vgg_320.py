@@ -1,0 +1,191 @@
+"""Drop-in for the hot-path half of the reference's ``nets/ron_vgg_320.py`` (lines 72-356):
+``RONParams``, ``RONNet.{anchors, bboxes_encode, bboxes_decode, bboxes_filter_min,
+detected_bboxes}``, ``ron_anchor_one_layer``, ``ron_anchors_all_layers`` -- same names,
+argument order, defaults and return structure, with torch CUDA tensors where the reference
+has TF tensors.  The network definition and the loss (reference :361-778) are out of scope.
+
+Additions (never replacements): ``RONNet.bboxes_encode_batch`` (padded batch of images,
+optional matched indices / objectness labels) and ``RONNet.detect`` (fused decode +
+objectness gate + select + NMS straight from the network outputs).
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from .. import core
+from . import ssd_common
+
+# reference: nets/ron_vgg_320.py:72-83
+RONParams = namedtuple('SSDParameters', ['img_shape', 'num_classes', 'no_annotation_label', 'feat_layers',
+                                         'feat_shapes', 'allowed_borders', 'anchor_sizes', 'anchor_ratios',
+                                         'anchor_steps', 'anchor_offset', 'prior_scaling'])
+
+
+class AnchorList(list):
+    """The list of per-layer (y, x, h, w) NumPy arrays the reference returns, carrying the
+    device-side anchor handle so bboxes_encode / bboxes_decode need no second upload."""
+    anchor_set = None
+
+
+def _anchor_set(kind, img_shape, layers_shape, anchor_sizes, anchor_ratios, anchor_steps, offset, borders):
+    return core.AnchorSet(kind, img_shape, layers_shape, anchor_sizes, anchor_ratios, anchor_steps, offset, borders)
+
+
+def ron_anchor_one_layer(img_shape, feat_shape, sizes, ratios, step, offset=0.5, dtype=np.float32):
+    """reference: nets/ron_vgg_320.py:285-333.  Returns y[H,W,1], x[H,W,1], h[A], w[A]."""
+    a = _anchor_set('ron', img_shape, [feat_shape], [sizes], [ratios], [step], offset, None)
+    y, x, h, w = a.as_reference_list()[0]
+    return y.astype(dtype), x.astype(dtype), h.astype(dtype), w.astype(dtype)
+
+
+def ron_anchors_all_layers(img_shape, layers_shape, anchor_sizes, anchor_ratios, anchor_steps, offset=0.5,
+                           dtype=np.float32, allowed_borders=None):
+    """reference: nets/ron_vgg_320.py:336-355 (``allowed_borders`` is an addition: it lets the
+    handle that rides on the returned list know the inside mask)."""
+    a = _anchor_set('ron', img_shape, layers_shape, anchor_sizes, anchor_ratios, anchor_steps, offset,
+                    allowed_borders)
+    out = AnchorList([tuple(v.astype(dtype) for v in t) for t in a.as_reference_list()])
+    out.anchor_set = a
+    return out
+
+
+class RONNet(object):
+    """reference: nets/ron_vgg_320.py:86-280 (hot-path methods only)."""
+    # reference: nets/ron_vgg_320.py:97-124
+    default_params = RONParams(
+        img_shape=(320, 320),
+        num_classes=21,
+        no_annotation_label=21,
+        feat_layers=['block7', 'block6', 'block5', 'block4'],
+        feat_shapes=[(5, 5), (10, 10), (20, 20), (40, 40)],
+        allowed_borders=[32, 16, 8, 4],
+        anchor_sizes=[(224., 256.), (160., 192.), (96., 128.), (32., 64.)],
+        anchor_ratios=[[1, 2, 3, 1. / 2, 1. / 3], [1, 2, 3, 1. / 2, 1. / 3],
+                       [1, 2, 3, 1. / 2, 1. / 3], [1, 2, 3, 1. / 2, 1. / 3]],
+        anchor_steps=[64, 32, 16, 8],
+        anchor_offset=0.5,
+        prior_scaling=[0.1, 0.1, 0.2, 0.2])
+
+    def __init__(self, params=None):
+        self.params = params if isinstance(params, RONParams) else RONNet.default_params
+        self._sets = {}
+
+    # ------------------------------------------------------------------ anchors
+    def _set_for(self, img_shape):
+        core._require_cuda()
+        key = (tuple(img_shape), torch.cuda.current_device())
+        if key not in self._sets:
+            p = self.params
+            self._sets[key] = _anchor_set('ron', img_shape, p.feat_shapes, p.anchor_sizes, p.anchor_ratios,
+                                          p.anchor_steps, p.anchor_offset, p.allowed_borders)
+        return self._sets[key]
+
+    def _resolve(self, anchors):
+        a = getattr(anchors, 'anchor_set', None)
+        if a is None:
+            a = self._set_for(self.params.img_shape)
+            if anchors is not None and len(anchors) != a.L:
+                raise IndexError('anchors: expected %d layers, got %d' % (a.L, len(anchors)))
+        return a
+
+    def anchors(self, img_shape, dtype=np.float32):
+        """reference: nets/ron_vgg_320.py:162-171."""
+        a = self._set_for(img_shape)
+        out = AnchorList([tuple(v.astype(dtype) for v in t) for t in a.as_reference_list()])
+        out.anchor_set = a
+        return out
+
+    # ------------------------------------------------------------------- encode
+    def bboxes_encode(self, labels, bboxes, anchors, positive_threshold=0.5, ignore_threshold=0.3, scope=None):
+        """reference: nets/ron_vgg_320.py:173-186 -> nets/ssd_common.py:337-414.  One image:
+        labels [G] int64, bboxes [G,4].  Returns 4 lists over layers: labels flat [n_l] int64,
+        localisations [H,W,A,4], scores flat [n_l], anchor corner boxes [H,W,A,4]."""
+        return ssd_common.tf_ssd_bboxes_encode(
+            labels, bboxes, anchors, self.params.num_classes, self.params.img_shape,
+            self.params.allowed_borders, self.params.no_annotation_label,
+            positive_threshold=positive_threshold, ignore_threshold=ignore_threshold,
+            prior_scaling=self.params.prior_scaling, scope=scope, _anchor_set=self._resolve(anchors))
+
+    def bboxes_encode_batch(self, labels, bboxes, counts, anchors=None, positive_threshold=0.5,
+                            ignore_threshold=0.3, want_matched=False, want_objness=False):
+        """Batched form: labels [B,Gmax] int64, bboxes [B,Gmax,4], counts [B] int32 ->
+        dict(labels [B,N], loc [B,N,4], scores [B,N], matched?, objness?)."""
+        return core.match_encode(self._resolve(anchors), bboxes, labels, counts, positive_threshold,
+                                 ignore_threshold, self.params.prior_scaling, want_matched=want_matched,
+                                 want_objness=want_objness)
+
+    # ------------------------------------------------------------------- decode
+    def bboxes_decode(self, feat_localizations, anchors, scope='ssd_bboxes_decode'):
+        """reference: nets/ron_vgg_320.py:188-195."""
+        return ssd_common.tf_ssd_bboxes_decode(feat_localizations, anchors, prior_scaling=self.params.prior_scaling,
+                                               scope=scope, _anchor_set=self._resolve(anchors))
+
+    def bboxes_filter_min(self, scores, bboxes, top_k, minsize=0.03, scope=None):
+        """reference: nets/ron_vgg_320.py:196-233.  Keeps boxes with w > minsize and h > minsize
+        (order preserving) and zero-pads to at least top_k.  The reference squeezes axis 0 and
+        therefore only accepts batch 1 (:221); here every image of the batch is filtered and the
+        result is padded to the longest row."""
+        if isinstance(scores, dict) or isinstance(bboxes, dict):
+            d_scores, d_bboxes = {}, {}
+            for c in scores.keys():
+                d_scores[c], d_bboxes[c] = self.bboxes_filter_min(scores[c], bboxes[c], top_k, minsize=minsize)
+            return d_scores, d_bboxes
+        s = core.as_cuda(scores, torch.float32)
+        b = core.as_cuda(bboxes, torch.float32, s.device)
+        # host-side compaction (dynamic shapes); the fused path (detected_bboxes / detect) never
+        # materialises this tensor -- the size test lives inside the select kernel.
+        h = b[..., 2] - b[..., 0]
+        w = b[..., 3] - b[..., 1]
+        mask = (w > np.float32(minsize)) & (h > np.float32(minsize))
+        width = max(int(mask.sum(-1).max().item()), int(top_k))
+        os_ = torch.zeros((s.shape[0], width), dtype=torch.float32, device=s.device)
+        ob = torch.zeros((s.shape[0], width, 4), dtype=torch.float32, device=s.device)
+        for i in range(s.shape[0]):
+            k = int(mask[i].sum().item())
+            os_[i, :k] = s[i][mask[i]]
+            ob[i, :k] = b[i][mask[i]]
+        return os_, ob
+
+    # ------------------------------------------------------------------ detect
+    def detected_bboxes(self, predictions, localisations, select_threshold=None, nms_threshold=0.5,
+                        clipping_bbox=None, top_k=400, keep_top_k=200):
+        """reference: nets/ron_vgg_320.py:234-256.  ``localisations`` are DECODED boxes (the
+        output of bboxes_decode), ``predictions`` the (already objectness-gated) class scores,
+        both lists over layers.  select -> clip -> min-size 0.03 -> sort top_k -> NMS('min').
+        Returns dicts class -> scores [B,keep_top_k], boxes [B,keep_top_k,4]."""
+        a = self._resolve(None)
+        s, b, _ = core.decode_select_topk(a, localisations, predictions, None, 0.0, select_threshold,
+                                          clipping_bbox, 0.03, top_k, self.params.prior_scaling,
+                                          loc_is_decoded=True)
+        return _nms_to_dicts(s, b, nms_threshold, keep_top_k)
+
+    def detect(self, predictions, feat_localizations, objness=None, objectness_threshold=0.03,
+               select_threshold=None, nms_threshold=0.5, clipping_bbox=None, top_k=400, keep_top_k=200,
+               minsize=0.03, mode='min', as_dict=False, want_idx=False):
+        """Fused eval post-process of eval_ron_network.py:226-236: raw localisations + class
+        scores (+ objectness) -> decode, objectness gate, select, clip, min-size, per-class top-k,
+        NMS.  Returns scores [B,C-1,M], boxes [B,C-1,M,4] (and anchor indices when asked)."""
+        a = self._resolve(None)
+        s, b, ix = core.decode_select_topk(a, feat_localizations, predictions, objness, objectness_threshold,
+                                           select_threshold, clipping_bbox, minsize, top_k,
+                                           self.params.prior_scaling, want_idx=want_idx)
+        B, CM, K = s.shape
+        ns, nb, ni = core.nms_batch(s.view(B * CM, K), b.view(B * CM, K, 4), nms_threshold, keep_top_k, mode,
+                                    assume_sorted=True, want_idx=want_idx)
+        ns, nb = ns.view(B, CM, -1), nb.view(B, CM, -1, 4)
+        if as_dict:
+            return {c + 1: ns[:, c] for c in range(CM)}, {c + 1: nb[:, c] for c in range(CM)}
+        if want_idx:
+            ni = ni.view(B, CM, -1).long()
+            aidx = torch.where(ni >= 0, torch.gather(ix.long(), 2, ni.clamp(min=0)), ni)
+            return ns, nb, aidx.int()
+        return ns, nb
+
+
+def _nms_to_dicts(s, b, nms_threshold, keep_top_k, mode='min'):
+    B, CM, K = s.shape
+    ns, nb, _ = core.nms_batch(s.view(B * CM, K), b.view(B * CM, K, 4), nms_threshold, keep_top_k, mode,
+                               assume_sorted=True)
+    ns, nb = ns.view(B, CM, -1), nb.view(B, CM, -1, 4)
+    return {c + 1: ns[:, c] for c in range(CM)}, {c + 1: nb[:, c] for c in range(CM)}

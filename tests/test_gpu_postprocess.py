@@ -1,0 +1,244 @@
+"""CUDA decode / select / top-k / NMS / TP-FP against the oracle and the golden vectors.
+Bar: bit-exact kept-box indices, order, scores and boxes."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import ron_oracle as O
+from ron_tensorflow_b200 import synth
+from _util import need_cuda, eq
+
+pytestmark = pytest.mark.gpu
+
+LS = [250, 1000, 4000, 16000]
+FS = [(5, 5), (10, 10), (20, 20), (40, 40)]
+APC = [10, 10, 10, 10]
+
+
+@pytest.fixture(scope='module')
+def ron():
+    need_cuda()
+    from ron_tensorflow_b200.nets import ron_vgg_320
+    net = ron_vgg_320.RONNet()
+    return net, net.anchors(net.params.img_shape)
+
+
+@pytest.fixture(scope='module')
+def dec_anchors():
+    return O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+
+
+def _layers(x, shaped=True):
+    return synth.split_layers(x, LS, FS if shaped else None, APC if shaped else None)
+
+
+def _golden_inputs(g, tag):
+    seed, hot, dense, K, M = [int(v) for v in g[tag + '_seed']]
+    loc, pred, obj = synth.make_predictions(seed, 1, 21250, 21, hot=hot, dense=bool(dense))
+    if hashlib.sha256(pred.tobytes()).digest() != g[tag + '_in_pred_sha'].tobytes():
+        pytest.skip('numpy Generator stream differs from the one that made the fixture')
+    return loc, pred, obj, K, M
+
+
+@pytest.mark.parametrize('tag', ['a', 'dense'])
+def test_detect_fused_golden(golden, ron, tag):
+    net, anchors = ron
+    g = golden('postprocess_ron320')
+    loc, pred, obj, K, M = _golden_inputs(g, tag)
+    from ron_tensorflow_b200 import core
+    s, b, _ = core.decode_select_topk(anchors.anchor_set, _layers(loc), _layers(pred), _layers(obj[..., None]), 0.03,
+                                      0.01, [0., 0., 1., 1.], 0.03, K)
+    eq(s, g[tag + '_topk_scores'], 'top-k scores')
+    eq(b, g[tag + '_topk_boxes'], 'top-k boxes')
+    ns, nb = net.detect(_layers(pred), _layers(loc), _layers(obj[..., None]), 0.03, 0.01, float(g[tag + '_nms_thr']),
+                        [0., 0., 1., 1.], K, M)
+    eq(ns, g[tag + '_scores'], 'nms scores')
+    eq(nb, g[tag + '_boxes'], 'nms boxes')
+
+
+def test_reference_call_sequence_golden(golden, ron):
+    """eval_ron_network.py:226-236 verbatim: bboxes_decode, objectness gate, detected_bboxes."""
+    import torch
+    net, anchors = ron
+    g = golden('postprocess_ron320')
+    loc, pred, obj, K, M = _golden_inputs(g, 'a')
+    localisations = net.bboxes_decode([torch.as_tensor(t).cuda() for t in _layers(loc)], anchors)
+    eq(torch.cat([t.reshape(1, -1, 4) for t in localisations], 1), g['a_decoded'], 'decoded')
+    filtered = [(torch.as_tensor(o).cuda() > 0.03).float() * torch.as_tensor(p).cuda()
+                for o, p in zip(_layers(obj[..., None]), _layers(pred))]
+    rscores, rbboxes = net.detected_bboxes(filtered, localisations, select_threshold=0.01,
+                                           nms_threshold=float(g['a_nms_thr']), clipping_bbox=[0., 0., 1., 1.],
+                                           top_k=K, keep_top_k=M)
+    assert sorted(rscores.keys()) == list(range(1, 21))
+    eq(torch.stack([rscores[c] for c in range(1, 21)], 1), g['a_scores'], 'scores')
+    eq(torch.stack([rbboxes[c] for c in range(1, 21)], 1), g['a_boxes'], 'boxes')
+
+
+def test_ssd_order_golden(golden, ron):
+    import torch
+    from ron_tensorflow_b200.nets import ssd_vgg_512
+    net, anchors = ron
+    g = golden('postprocess_ron320')
+    loc, pred, obj, K, M = _golden_inputs(g, 'a')
+    dec = net.bboxes_decode(_layers(loc), anchors)
+    ssd = ssd_vgg_512.SSDNet()
+    ssd._sets[((512, 512), torch.cuda.current_device())] = anchors.anchor_set   # RON-shaped tensors, SSD pipeline
+    rs, rb = ssd.detected_bboxes(_layers(pred), dec, select_threshold=0.25, nms_threshold=0.45, top_k=100,
+                                 keep_top_k=50)
+    eq(torch.stack([rs[c] for c in range(1, 21)], 1), g['ssd_scores'], 'scores')
+    eq(torch.stack([rb[c] for c in range(1, 21)], 1), g['ssd_boxes'], 'boxes')
+
+
+@pytest.mark.parametrize('dense,K,M,thr,mode', [(False, 400, 200, 0.45, 'min'), (False, 400, 200, 0.45, 'union'),
+                                                (True, 400, 200, 0.45, 'min'), (False, 37, 11, 0.3, 'min')])
+def test_detect_batch_vs_oracle(ron, dec_anchors, dense, K, M, thr, mode):
+    net, anchors = ron
+    B = 3
+    loc, pred, obj = synth.make_predictions(77 + int(dense), B, 21250, 21, hot=300, dense=dense)
+    ns, nb, ni = net.detect(_layers(pred, False), _layers(loc, False), _layers(obj, False), 0.03, 0.01, thr,
+                            [0., 0., 1., 1.], K, M, mode=mode, want_idx=True)
+    for b in range(B):
+        o = O.detected_bboxes_image(pred[b], loc[b], dec_anchors, obj[b], 0.03, 0.01, thr, [0., 0., 1., 1.], K, M,
+                                    mode=mode)
+        eq(ni[b], o['idx'], 'kept anchor indices b=%d' % b)
+        eq(ns[b], o['scores'], 'scores b=%d' % b)
+        eq(nb[b], o['boxes'], 'boxes b=%d' % b)
+
+
+def test_detect_81_classes(ron, dec_anchors):
+    """config 5 shape: 81 classes (different shared-memory tile, 3 ballot words)."""
+    net, anchors = ron
+    loc, pred, obj = synth.make_predictions(99, 2, 21250, 81, hot=500)
+    ns, nb, ni = net.detect(_layers(pred, False), _layers(loc, False), _layers(obj, False), 0.03, 0.005, 0.45,
+                            [0., 0., 1., 1.], 200, 100, want_idx=True)
+    for b in range(2):
+        o = O.detected_bboxes_image(pred[b], loc[b], dec_anchors, obj[b], 0.03, 0.005, 0.45, [0., 0., 1., 1.], 200, 100)
+        eq(ni[b], o['idx'], 'idx')
+        eq(ns[b], o['scores'], 'scores')
+        eq(nb[b], o['boxes'], 'boxes')
+
+
+@pytest.mark.parametrize('mode', ['min', 'union'])
+@pytest.mark.parametrize('thr,M', [(0.45, 200), (0.3, 20), (0.7, 64)])
+def test_bboxes_nms_golden(golden, mode, thr, M):
+    need_cuda()
+    import ron_tensorflow_b200.tf_extended as tfe
+    g = golden('nms')
+    s, b = tfe.bboxes_nms(g['in_scores'], g['in_boxes'], nms_threshold=thr, keep_top_k=M, mode=mode)
+    eq(s, g['%s_%g_%d_scores' % (mode, thr, M)], 'scores')
+    eq(b, g['%s_%g_%d_boxes' % (mode, thr, M)], 'boxes')
+
+
+def test_nms_batch_sort_clip_golden(golden):
+    need_cuda()
+    import ron_tensorflow_b200.tf_extended as tfe
+    g = golden('nms')
+    sc = np.stack([g['in_scores'], g['in_scores'][::-1]])
+    bx = np.stack([g['in_boxes'], g['in_boxes'][::-1]])
+    s, b = tfe.bboxes_nms_batch(sc, bx, nms_threshold=0.45, keep_top_k=32)
+    eq(s, g['batch_scores'], 'batch scores')
+    eq(b, g['batch_boxes'], 'batch boxes')
+    d_s, d_b = tfe.bboxes_nms_batch({3: sc, 7: sc[::-1].copy()}, {3: bx, 7: bx[::-1].copy()}, 0.45, 32)
+    eq(d_s[3], g['batch_scores'], 'dict scores')
+    eq(d_b[7], g['batch_boxes'][::-1], 'dict boxes')
+    ss, sb = tfe.bboxes_sort(g['in_scores'][None], g['in_boxes'][None], top_k=50)
+    eq(ss, g['sort_scores'], 'sort scores')
+    eq(sb, g['sort_boxes'], 'sort boxes')
+    eq(tfe.bboxes_clip([0., 0., 1., 1.], g['clip_in']), g['clip_out'], 'clip')
+    with pytest.raises(ValueError):
+        tfe.bboxes_sort(g['in_scores'][None], g['in_boxes'][None], top_k=500)    # tf.nn.top_k(k > N)
+    with pytest.raises(ValueError):
+        tfe.bboxes_nms(g['in_scores'], g['in_boxes'], mode='iou')              # bboxes.py:210
+
+
+@pytest.mark.parametrize('K,M,mode', [(400, 200, 'min'), (400, 200, 'union'), (1000, 50, 'min'), (33, 40, 'min'),
+                                      (2500, 300, 'union')])
+def test_nms_random_vs_oracle(K, M, mode):
+    need_cuda()
+    from ron_tensorflow_b200 import core
+    rng = np.random.Generator(np.random.PCG64(K * 7 + M))
+    S = 6
+    c = rng.uniform(0.1, 0.9, size=(S, K, 2))
+    sz = np.exp(rng.uniform(np.log(0.02), np.log(0.5), size=(S, K, 2)))
+    boxes = np.concatenate([c - sz / 2, c + sz / 2], -1).astype(np.float32)
+    scores = rng.uniform(0.01, 1, size=(S, K)).astype(np.float32)
+    scores[:, ::7] = scores[:, 1::7][:, :scores[:, ::7].shape[1]]       # ties
+    scores[0, K // 2:] = 0
+    boxes[0, K // 2:] = 0
+    s, b, ix = core.nms_batch(scores, boxes, 0.45, M, mode, want_idx=True)
+    os_, ob, oi = O.nms_batch(scores, boxes, 0.45, M, mode)
+    eq(ix, oi, 'kept positions')
+    eq(s, os_, 'scores')
+    eq(b, ob, 'boxes')
+
+
+def test_tpfp_golden_and_random(golden):
+    need_cuda()
+    import torch
+    import ron_tensorflow_b200.tf_extended as tfe
+    g = golden('tpfp')
+    d_s = {c: g['det_scores_%d' % c] for c in (1, 2, 3)}
+    d_b = {c: g['det_boxes_%d' % c] for c in (1, 2, 3)}
+    n, tp, fp, _ = tfe.bboxes_matching_batch(d_s.keys(), d_s, d_b, g['glabels'], g['gboxes'], g['gdiff'],
+                                             matching_threshold=0.5)
+    state = None
+    for c in (1, 2, 3):
+        eq(n[c], g['n_gt_%d' % c], 'n_gt')
+        eq(tp[c], g['tp_%d' % c], 'tp')
+        eq(fp[c], g['fp_%d' % c], 'fp')
+    vals, state = tfe.streaming_tp_fp_arrays(n, tp, fp, {c: torch.as_tensor(v) for c, v in d_s.items()})
+    for c in (1, 2, 3):
+        prec, rec = tfe.precision_recall(*vals[c])
+        eq(prec, g['prec_%d' % c], 'precision')
+        eq(rec, g['rec_%d' % c], 'recall')
+        assert abs(tfe.average_precision_voc07(prec, rec) - float(g['ap07_%d' % c])) < 1e-12
+        assert abs(tfe.average_precision_voc12(prec, rec) - float(g['ap12_%d' % c])) < 1e-12
+    # single-problem form (bboxes.py:316-404)
+    n1, tp1, fp1 = tfe.bboxes_matching(2, d_s[2][1], d_b[2][1], g['glabels'][1], g['gboxes'][1], g['gdiff'][1])
+    assert int(n1) == int(g['n_gt_2'][1])
+    eq(tp1, g['tp_2'][1], 'single tp')
+    eq(fp1, g['fp_2'][1], 'single fp')
+    # random, 20 classes, 70 GT (more than one lane pass)
+    from ron_tensorflow_b200 import core
+    rng = np.random.Generator(np.random.PCG64(5))
+    B, CM, M, G = 4, 20, 50, 70
+    gb, gl, cnt = synth.make_gt_batch(8, B, 30, G, g_max=G)
+    gd = (rng.uniform(size=(B, G)) < 0.2).astype(np.int64)
+    src = rng.integers(0, G, size=(B, CM, M))
+    det = np.take_along_axis(gb[:, None].repeat(CM, 1), src[..., None].repeat(4, -1), 2)
+    det = (det + rng.normal(0, 0.02, size=det.shape)).astype(np.float32)
+    sc = np.sort(rng.uniform(0, 1, size=(B, CM, M)).astype(np.float32), -1)[..., ::-1].copy()
+    n, tp, fp = core.tpfp_match(sc, det, gl, gb, gd, 0.5)
+    for b in range(B):
+        for c in range(CM):
+            on, otp, ofp = O.bboxes_matching(c + 1, sc[b, c], det[b, c], gl[b], gb[b], gd[b])
+            assert int(n[b, c]) == on
+            eq(tp[b, c], otp, 'tp b=%d c=%d' % (b, c))
+            eq(fp[b, c], ofp, 'fp b=%d c=%d' % (b, c))
+
+
+def test_fine_grained_functions(golden):
+    """areas / intersection / iou_matrix / do_dual_max_match / select / jaccard one to one."""
+    need_cuda()
+    import torch
+    from ron_tensorflow_b200.nets import ssd_common
+    import ron_tensorflow_b200.tf_extended as tfe
+    g = golden('dual_max_match')
+    for ib in (1, 0):
+        for gf in (1, 0):
+            m, s = ssd_common.do_dual_max_match(g['ov'], 0.5, 0.3, ignore_between=bool(ib), gt_max_first=bool(gf))
+            eq(m, g['m_%d%d' % (ib, gf)], 'matched %d%d' % (ib, gf))
+            eq(s, g['s_%d%d' % (ib, gf)], 'scores %d%d' % (ib, gf))
+    gt, _ = synth.make_gt(3, 9)
+    _, cor, _ = O.encode_anchor_tables(O.anchors_all_layers(O.RON320), (320, 320), [32, 16, 8, 4])
+    eq(ssd_common.iou_matrix(gt, cor), O.iou_matrix(gt, cor), 'iou_matrix')
+    eq(ssd_common.areas(gt)[:, 0], O._areas(gt), 'areas')
+    eq(tfe.bboxes_jaccard(gt[0], cor), O.bboxes_jaccard(gt[0], cor), 'jaccard')
+    loc, pred, obj = synth.make_predictions(3, 2, 500, 21)
+    d_s, d_b = ssd_common.tf_ssd_bboxes_select_layer(pred, loc, select_threshold=0.02)
+    for c in (1, 7, 20):
+        m = (pred[:, :, c] > np.float32(0.02)).astype(np.float32)
+        eq(d_s[c], pred[:, :, c] * m, 'select scores')
+        eq(d_b[c], loc * m[..., None], 'select boxes')
+    assert 0 not in d_s and len(d_s) == 20
