@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the detection hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference's CPU path (NumPy restatement), host cores
+
+One JSON line on rank 0.  Headline (`value`): images/sec of BASELINE.json configs[1] -- RON-320
+training-target path (joint match + encode), batch 64 per GPU, 1-50 GT boxes per image, inputs
+resident in HBM.  `stages.postprocess` carries the second half of the metric, configs[2]: RON-320
+eval post-process, batch 256 per GPU (decode + objectness gate + per-class top-400 + NMS 0.45 keep
+200, then VOC TP/FP and one NCCL gather at the end of the run).  A "step" is one pass of the path
+over one batch.  Scaling is weak: every rank owns its own batch (images shard with no data-path
+collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENC_B, ENC_G = 64, (1, 50)
+POST_B, POST_K, POST_M, POST_THR = 256, 400, 200, 0.45
+N_ANCHORS, N_CLASSES = 21250, 21
+ENC_BYTES_PER_IMAGE = N_ANCHORS * 28          # labels i64 + loc 4xf32 + score f32; + 24 B per GT
+POST_BYTES_PER_IMAGE = N_ANCHORS * (4 * N_CLASSES + 16 + 4) + (N_CLASSES - 1) * POST_M * 20
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(',')]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def _enc_worker(args):
+    from oracle import ron_oracle as O
+    global _ENC_TABLES
+    try:
+        enc, cor, inside = _ENC_TABLES
+    except NameError:
+        enc, cor, inside = _ENC_TABLES = O.encode_anchor_tables(O.anchors_all_layers(O.RON320), (320, 320), [32, 16, 8, 4])
+    boxes, labels = args
+    r = O.encode_image(labels, boxes, enc, cor, inside, 0.56, 0.3)
+    return int((r['labels'] > 0).sum())
+
+
+def _post_worker(args):
+    from oracle import ron_oracle as O
+    global _DEC_ANCH
+    try:
+        dec = _DEC_ANCH
+    except NameError:
+        dec = _DEC_ANCH = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+    pred, loc, obj = args
+    r = O.detected_bboxes_image(pred, loc, dec, obj, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+    return int((r['scores'] > 0).sum())
+
+
+def _enc_items(n_images):
+    from ron_tensorflow_b200 import synth
+    boxes, labels, counts = synth.make_gt_batch(2, n_images, ENC_G[0], ENC_G[1])
+    return [(boxes[b, :counts[b]], labels[b, :counts[b]]) for b in range(n_images)]
+
+
+def _post_items(n_images):
+    from ron_tensorflow_b200 import synth
+    loc, pred, obj = synth.make_predictions(3000, n_images, N_ANCHORS, N_CLASSES, hot=300)
+    return [(pred[b], loc[b], obj[b]) for b in range(n_images)]
+
+
+def cpu_encode_sample(n_images, procs=1):
+    """oracle match+encode on the first n_images of the configs[1] workload, single thread."""
+    items = _enc_items(n_images)
+    _enc_worker(items[0])
+    t0 = time.perf_counter()
+    for it in items:
+        _enc_worker(it)
+    return n_images / (time.perf_counter() - t0)
+
+
+def cpu_post_sample(n_images, procs=1):
+    items = _post_items(n_images)
+    t0 = time.perf_counter()
+    for it in items:
+        _post_worker(it)
+    return n_images / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores.  TensorFlow 1.x is
+    not installable here, so this is the op-for-op NumPy restatement (oracle/, kind 'port'),
+    one worker process per host core (the reference itself feeds the encode from 24 queue-runner
+    threads, ron_net.py:73-75), each step a bounded sample of the same workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_enc = ((max(ENC_B, 2 * cores) + ENC_B - 1) // ENC_B) * ENC_B      # whole batches, >= 2 images per core
+    items = _enc_items(n_enc)
+    n_post = max(cores, 8)
+    pitems = _post_items(n_post)
+    with mp.get_context('fork').Pool(cores) as pool:
+        times = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_enc_worker, items, chunksize=1)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        v_enc = n_enc * len(times) / sum(times)
+        pool.map(_post_worker, pitems[:cores], chunksize=1)
+        t0 = time.perf_counter()
+        pool.map(_post_worker, pitems, chunksize=1)
+        v_post = n_post / (time.perf_counter() - t0)
+    line = {
+        'impl': 'reference', 'metric': 'images/sec (match+encode)', 'value': v_enc, 'unit': 'images/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[1]: RON-320 joint match+encode, 1-50 GT/image, thresholds 0.56/0.3 '
+                               '(CPU: NumPy restatement of the reference TF-1 graph, %d images per step)' % n_enc},
+        'cpu_baseline': {'value': v_enc, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d images per step x %d steps, %d worker processes' % (n_enc, args.steps, cores)},
+        'e2e': {'value': v_enc, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+        'stages': {'postprocess': {'value': v_post, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                   'sample': '%d images, decode+gate+top-400+NMS(0.45,keep 200)' % n_post}},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def timed_steps(torch, fn, steps, warmup, flush=None):
+    """W untimed warm-ups, then exactly `steps` steps, each bracketed by CUDA events on the
+    launching (current) stream; an L2 flush (not timed) runs between steps when given."""
+    for _ in range(warmup):
+        fn()
+        if flush is not None:
+            flush.zero_()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        if flush is not None:
+            flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]      # ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ron_tensorflow_b200 import core, synth
+    from ron_tensorflow_b200.nets import ron_vgg_320
+    import ron_tensorflow_b200.tf_extended as tfe
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    hbm, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    net = ron_vgg_320.RONNet()
+    anchors = net.anchors(net.params.img_shape)
+    aset = anchors.anchor_set
+    N = aset.N
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # ---------------------------------------------------------------- stage A: match + encode
+    boxes, labels, counts = synth.make_gt_batch(2, ENC_B, ENC_G[0], ENC_G[1], first_image=rank * ENC_B)
+    d_boxes = torch.from_numpy(boxes).to(dev)
+    d_labels = torch.from_numpy(labels).to(dev)
+    d_counts = torch.from_numpy(counts).to(dev)
+    out = dict(labels=torch.empty((ENC_B, N), dtype=torch.int64, device=dev),
+               loc=torch.empty((ENC_B, N, 4), dtype=torch.float32, device=dev),
+               scores=torch.empty((ENC_B, N), dtype=torch.float32, device=dev))
+
+    def enc_step():
+        core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, out=out)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = core.launch_count()
+    ms = timed_steps(torch, enc_step, args.steps, args.warmup, flush)
+    enc_launches = core.launch_count() - l0
+    barrier()
+    t_enc = max_over_ranks(sum(ms) / 1e3)
+    enc_value = ENC_B * args.steps * world / t_enc
+    enc_bytes = ENC_B * ENC_BYTES_PER_IMAGE + int(counts.sum()) * 24
+    enc_achieved = enc_bytes / (np.mean(ms) * 1e-3) / 1e9
+
+    # e2e: pinned host GT -> device, kernels, targets back to pinned host memory, every step
+    h_boxes = torch.from_numpy(boxes).pin_memory()
+    h_labels = torch.from_numpy(labels).pin_memory()
+    h_counts = torch.from_numpy(counts).pin_memory()
+    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+
+    def enc_e2e_step():
+        d_boxes.copy_(h_boxes, non_blocking=True)
+        d_labels.copy_(h_labels, non_blocking=True)
+        d_counts.copy_(h_counts, non_blocking=True)
+        r = net.bboxes_encode_batch(d_labels, d_boxes, d_counts, anchors, 0.56, 0.3)
+        for k in h_out:
+            h_out[k].copy_(r[k], non_blocking=True)
+
+    barrier()
+    ms_e2e = timed_steps(torch, enc_e2e_step, args.steps, args.warmup)
+    barrier()
+    t_e2e = max_over_ranks(sum(ms_e2e) / 1e3)
+    enc_e2e = ENC_B * args.steps * world / t_e2e
+    enc_h2d = boxes.nbytes + labels.nbytes + counts.nbytes
+    enc_d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+
+    # ---------------------------------------------------------------- stage B: eval post-process
+    post = None
+    if not args.no_postprocess:
+        ls = aset.layer_sizes
+        loc, pred, obj = synth.make_predictions(3000 + rank, POST_B, N, N_CLASSES, hot=300)
+        gboxes, glabels, gcounts = synth.make_gt_batch(3, POST_B, 1, 12, g_max=12, first_image=rank * POST_B)
+        gdiff = np.zeros_like(glabels)
+        h_loc = [torch.from_numpy(t).pin_memory() for t in synth.split_layers(loc, ls)]
+        h_pred = [torch.from_numpy(t).pin_memory() for t in synth.split_layers(pred, ls)]
+        h_obj = [torch.from_numpy(t).pin_memory() for t in synth.split_layers(obj, ls)]
+        d_loc = [t.to(dev) for t in h_loc]
+        d_pred = [t.to(dev) for t in h_pred]
+        d_obj = [t.to(dev) for t in h_obj]
+        d_gl, d_gb, d_gd = (torch.from_numpy(a).to(dev) for a in (glabels, gboxes, gdiff))
+        res = {}
+
+        def post_step():
+            ns, nb = net.detect(d_pred, d_loc, d_obj, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+            res['s'], res['b'] = ns, nb
+            res['tpfp'] = core.tpfp_match(ns, nb, d_gl, d_gb, d_gd, 0.5)
+
+        barrier()
+        l1 = core.launch_count()
+        ms_p = timed_steps(torch, post_step, args.steps, args.warmup)       # inputs (586 MB) exceed L2
+        post_launches = core.launch_count() - l1
+        barrier()
+        t_post = max_over_ranks(sum(ms_p) / 1e3)
+        post_value = POST_B * args.steps * world / t_post
+        post_achieved = POST_B * POST_BYTES_PER_IMAGE / (np.mean(ms_p) * 1e-3) / 1e9
+
+        h_s = torch.empty((POST_B, N_CLASSES - 1, POST_M), dtype=torch.float32).pin_memory()
+        h_b = torch.empty((POST_B, N_CLASSES - 1, POST_M, 4), dtype=torch.float32).pin_memory()
+
+        def post_e2e_step():
+            for d, h in zip(d_loc + d_pred + d_obj, h_loc + h_pred + h_obj):
+                d.copy_(h, non_blocking=True)
+            ns, nb = net.detect(d_pred, d_loc, d_obj, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+            h_s.copy_(ns, non_blocking=True)
+            h_b.copy_(nb, non_blocking=True)
+
+        barrier()
+        ms_pe = timed_steps(torch, post_e2e_step, max(3, args.steps // 4), 3)
+        barrier()
+        t_pe = max_over_ranks(sum(ms_pe) / 1e3)
+        post_e2e = POST_B * len(ms_pe) * world / t_pe
+
+        # VOC TP/FP records: accumulated on every rank, gathered ONCE with NCCL, AP on rank 0
+        n_gt, tp, fp = res['tpfp']
+        cls = list(range(1, N_CLASSES))
+        vals, state = tfe.streaming_tp_fp_arrays({c: n_gt[:, c - 1] for c in cls}, {c: tp[:, c - 1] for c in cls},
+                                                 {c: fp[:, c - 1] for c in cls}, {c: res['s'][:, c - 1] for c in cls})
+        barrier()
+        g0 = time.perf_counter()
+        merged = tfe.gather_tp_fp(state, N_CLASSES)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        aps = []
+        for c in cls:
+            v = merged[c].value()
+            p_, r_ = tfe.precision_recall(*v)
+            aps.append(tfe.average_precision_voc07(p_, r_))
+        post = {
+            'metric': 'images/sec (decode+select+NMS)', 'value': post_value, 'unit': 'images/s',
+            'ms_per_step': float(np.mean(ms_p)),
+            'config': {'workload': 'BASELINE configs[2]: RON-320 eval post-process, batch %d per GPU, objectness 0.03, '
+                                   'select 0.01, clip, min-size 0.03, top-k %d, NMS min-area %.2f keep %d, + VOC TP/FP kernel'
+                                   % (POST_B, POST_K, POST_THR, POST_M), 'l2': 'inputs (586 MB) exceed L2'},
+            'roofline': {'bound': 'hbm', 'achieved': post_achieved, 'peak': hbm, 'unit': 'GB/s',
+                         'frac': post_achieved / hbm, 'traffic': None, 'peak_source': peak_src,
+                         'note': 'algorithmic 2.29 MB/image over the whole step (3 select + 1 NMS + 1 TP/FP launches)'},
+            'e2e': {'value': post_e2e, 'unit': 'images/s',
+                    'h2d_bytes_per_step': int(sum(t.numel() * 4 for t in h_loc + h_pred + h_obj)),
+                    'd2h_bytes_per_step': int(h_s.numel() * 4 + h_b.numel() * 4)},
+            'gpu_launches': post_launches,
+            'tpfp_gather': {'backend': 'nccl' if world > 1 else 'none', 'ms': gather_ms, 'mAP_voc07_synthetic': float(np.mean(aps)),
+                            'records': int(sum(merged[c].scores.shape[0] for c in cls))},
+        }
+    clocks = sampler.stop()
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n = 128
+        v = cpu_encode_sample(n, 1)
+        cpu = {'value': v, 'unit': 'images/s', 'cores': 1, 'kind': 'port',
+               'sample': 'first %d images of the workload, oracle (NumPy restatement of the TF-1 graph), 1 thread' % n}
+        if post is not None:
+            n2 = 24
+            post['cpu_baseline'] = {'value': cpu_post_sample(n2, 1), 'unit': 'images/s', 'cores': 1, 'kind': 'port',
+                                    'sample': '%d images, oracle, 1 thread' % n2}
+
+    if rank == 0:
+        line = {
+            'metric': 'images/sec (match+encode)', 'value': enc_value, 'unit': 'images/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(ms)), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[1]: RON-320 joint match+encode over all 4 layers (21250 anchors), '
+                                   'batch %d per GPU, 1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels'
+                                   % ENC_B, 'l2': 'flushed between timed steps (256 MB write)'},
+            'roofline': {'bound': 'hbm', 'achieved': enc_achieved, 'peak': hbm, 'unit': 'GB/s',
+                         'frac': enc_achieved / hbm, 'traffic': None, 'peak_source': peak_src,
+                         'note': 'algorithmic %d B/batch over the whole step (match_encode_kernel + match_force_kernel)'
+                                 % enc_bytes},
+            'cpu_baseline': cpu,
+            'e2e': {'value': enc_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': int(enc_h2d),
+                    'd2h_bytes_per_step': int(enc_d2h)},
+            'gpu_launches': int(enc_launches),
+            'clocks': clocks,
+            'stages': {'postprocess': post},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-postprocess', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -44,7 +44,7 @@ def as_cuda(x, dtype, device=None):
 class _DevView(object):
     """Zero-copy torch view of device memory owned by an anchor handle."""
     def __init__(self, ptr, shape, typestr, owner):
-        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), True),
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
                                          'version': 2}
         self._owner = owner
 
