@@ -3,6 +3,7 @@
 // nets/ssd_common.py:371-402 (re-derived encode anchors, per-anchor borders) and :103-115
 // (second-trip corners, inside mask).  SURVEY.md Appendix A.1-A.3.
 #include <math.h>
+#include <math_constants.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,7 +24,8 @@ struct AnchorGenParams {
 // reference evaluates them in Python double and stores to a float32 array).
 __global__ void __launch_bounds__(256)
 anchor_gen_kernel(const __grid_constant__ AnchorGenParams p, float4* __restrict__ dec,
-                  float4* __restrict__ enc, float4* __restrict__ cor, uint8_t* __restrict__ inside) {
+                  float4* __restrict__ enc, float4* __restrict__ cor, uint8_t* __restrict__ inside,
+                  float4* __restrict__ mcor) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.tab.N) return;
     int l = layer_of(p.tab, n);
@@ -51,12 +53,14 @@ anchor_gen_kernel(const __grid_constant__ AnchorGenParams p, float4* __restrict_
     if (p.has_border)
         in = (ymin >= p.lo_y[l]) && (xmin >= p.lo_x[l]) && (ymax < p.hi_y[l]) && (xmax < p.hi_x[l]);
     inside[n] = in ? 1 : 0;
+    mcor[n] = in ? make_float4(ymin, xmin, ymax, xmax)
+                 : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 }
 
 // Arbitrary flattened anchors: corners + inside mask from given (y, x, h, w) and per-anchor borders.
 __global__ void __launch_bounds__(256)
 anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ border, int N, int img_h, int img_w,
-                   float4* __restrict__ cor, uint8_t* __restrict__ inside) {
+                   float4* __restrict__ cor, uint8_t* __restrict__ inside, float4* __restrict__ mcor) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float4 a = yxhw[n];
@@ -70,6 +74,8 @@ anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ bord
         in = (ymin >= lo_y) && (xmin >= lo_x) && (ymax < hi_y) && (xmax < hi_x);
     }
     inside[n] = in ? 1 : 0;
+    mcor[n] = in ? make_float4(ymin, xmin, ymax, xmax)
+                 : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 }
 
 }  // namespace ronk
@@ -102,13 +108,14 @@ extern "C" int ronk_anchors_create_flat(int img_h, int img_w, int N, const float
     if (e == cudaSuccess) e = cudaMalloc(&h->d_enc, (size_t)N * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cor, (size_t)N * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_inside, (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_mcor, (size_t)N * 16);
     if (e == cudaSuccess && border) e = cudaMalloc(&d_border, (size_t)N * 4);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_dec, yxhw, (size_t)N * 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_enc, yxhw, (size_t)N * 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && border) e = cudaMemcpy(d_border, border, (size_t)N * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         anchor_flat_kernel<<<(N + 255) / 256, 256>>>((const float4*)h->d_enc, d_border, N, img_h, img_w,
-                                                     (float4*)h->d_cor, h->d_inside);
+                                                     (float4*)h->d_cor, h->d_inside, (float4*)h->d_mcor);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
@@ -219,9 +226,10 @@ extern "C" int ronk_anchors_create(int kind, int img_h, int img_w, int num_layer
     if (e == cudaSuccess) e = cudaMalloc(&h->d_enc, (size_t)n * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cor, (size_t)n * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_inside, (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_mcor, (size_t)n * 16);
     if (e == cudaSuccess) {
         anchor_gen_kernel<<<(n + 255) / 256, 256>>>(*p, (float4*)h->d_dec, (float4*)h->d_enc,
-                                                    (float4*)h->d_cor, h->d_inside);
+                                                    (float4*)h->d_cor, h->d_inside, (float4*)h->d_mcor);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
@@ -242,6 +250,7 @@ extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
     if (h->d_enc) cudaFree(h->d_enc);
     if (h->d_cor) cudaFree(h->d_cor);
     if (h->d_inside) cudaFree(h->d_inside);
+    if (h->d_mcor) cudaFree(h->d_mcor);
     delete h;
 }
 

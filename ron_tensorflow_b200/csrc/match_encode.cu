@@ -21,11 +21,11 @@
 namespace ronk {
 
 constexpr int kEncThreads = 256;
-constexpr int kEncWarps = kEncThreads / 32;
 constexpr int kEncApt = 2;   // anchors per thread
 
 struct EncodeParams {
     const float4* cor;
+    const float4* mcor;
     const float4* enc;
     const uint8_t* inside;
     int N;
@@ -60,39 +60,33 @@ __device__ __forceinline__ float4 encode_loc(float4 gb, float4 e, const EncodePa
 }
 
 template <int APT>
-__global__ void __launch_bounds__(kEncThreads)
+__global__ void __launch_bounds__(kEncThreads, 4)
 match_encode_kernel(const __grid_constant__ EncodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* s_box = reinterpret_cast<float4*>(smem);
-    u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);
-    float* s_area = reinterpret_cast<float*>(s_best + p.gcap);
-    int* s_gid = reinterpret_cast<int*>(s_area + p.gcap);
-    __shared__ float s_red[4][kEncWarps];
-    __shared__ int s_wcnt[kEncWarps];
+    float4* s_box = reinterpret_cast<float4*>(smem);              // [gcap] GT corners
+    u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [gcap] per-GT (iou bits, ~anchor) of this tile
+    float* s_area = reinterpret_cast<float*>(s_best + p.gcap);    // [gcap]
 
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int warp_n0 = blockIdx.x * (kEncThreads * APT) + warp * (32 * APT);
 
-    // ---- this thread's anchors: corners + area in registers for the whole image loop.
-    // Anchors outside the border mask have overlap 0 with everything (ssd_common.py:118):
-    // give them an empty box so they never produce a positive intersection.
+    // ---- this thread's anchors: corners + area in registers for the whole image loop.  The
+    // match table already holds an empty box (+inf,+inf,-inf,-inf) for anchors outside the
+    // border mask: their overlap with everything is exactly 0 (ssd_common.py:118).
     float4 a[APT];
     float area[APT];
     float wy0 = CUDART_INF_F, wx0 = CUDART_INF_F, wy1 = -CUDART_INF_F, wx1 = -CUDART_INF_F;
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
         int n = warp_n0 + j * 32 + lane;
-        a[j] = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-        area[j] = 0.f;
-        if (n < p.N && p.inside[n]) {
-            a[j] = p.cor[n];
-            area[j] = (a[j].w - a[j].y) * (a[j].z - a[j].x);
-            wy0 = fminf(wy0, a[j].x);
-            wx0 = fminf(wx0, a[j].y);
-            wy1 = fmaxf(wy1, a[j].z);
-            wx1 = fmaxf(wx1, a[j].w);
-        }
+        a[j] = (n < p.N) ? p.mcor[n] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        const bool in = a[j].x != CUDART_INF_F;          // false only for the empty box
+        area[j] = in ? (a[j].w - a[j].y) * (a[j].z - a[j].x) : 0.f;
+        wy0 = fminf(wy0, a[j].x);
+        wx0 = fminf(wx0, a[j].y);
+        wy1 = fmaxf(wy1, a[j].z);
+        wx1 = fmaxf(wx1, a[j].w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -101,104 +95,92 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
         wy1 = fmaxf(wy1, __shfl_xor_sync(full, wy1, o));
         wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
     }
-    if (lane == 0) {
-        s_red[0][warp] = wy0;
-        s_red[1][warp] = wx0;
-        s_red[2][warp] = wy1;
-        s_red[3][warp] = wx1;
-    }
-    __syncthreads();
-    float ty0 = s_red[0][0], tx0 = s_red[1][0], ty1 = s_red[2][0], tx1 = s_red[3][0];
-#pragma unroll
-    for (int w = 1; w < kEncWarps; ++w) {
-        ty0 = fminf(ty0, s_red[0][w]);
-        tx0 = fminf(tx0, s_red[1][w]);
-        ty1 = fmaxf(ty1, s_red[2][w]);
-        tx1 = fmaxf(tx1, s_red[3][w]);
-    }
 
-    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
-        int G = p.gt_counts[b];
+    // software prefetch of the next image's GT boxes (one per thread; G > 256 reads the rest late)
+    int b = blockIdx.y;
+    int G = 0;
+    float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < p.B) {
+        G = p.gt_counts[b];
         G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
+        if (tid < G) gb = p.gt_boxes[(size_t)b * p.Gmax + tid];
+    }
+    for (; b < p.B;) {
         const float4* gtb = p.gt_boxes + (size_t)b * p.Gmax;
-
-        // ---- order-preserving cull of the GT list against the tile's bounding box.  A pair
-        // has a positive intersection only if the GT overlaps the union extent of the tile
-        // (float subtraction is sign exact), every other pair contributes exactly 0.
-        __syncthreads();
-        int ncull = 0;
-        for (int g0 = 0; g0 < G; g0 += kEncThreads) {
-            int g = g0 + tid;
-            bool pass = false;
-            float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < G) {
-                gb = gtb[g];
-                pass = (fminf(gb.z, ty1) > fmaxf(gb.x, ty0)) && (fminf(gb.w, tx1) > fmaxf(gb.y, tx0));
-            }
-            unsigned bal = __ballot_sync(full, pass);
-            if (lane == 0) s_wcnt[warp] = __popc(bal);
-            __syncthreads();
-            int off = ncull, tot = 0;
-#pragma unroll
-            for (int w = 0; w < kEncWarps; ++w) {
-                int c = s_wcnt[w];
-                if (w < warp) off += c;
-                tot += c;
-            }
-            if (pass) {
-                int k = off + __popc(bal & ((1u << lane) - 1u));
-                s_box[k] = gb;
-                s_area[k] = (gb.w - gb.y) * (gb.z - gb.x);
-                s_gid[k] = g;
-                s_best[k] = 0ull;
-            }
-            ncull += tot;
-            __syncthreads();
+        __syncthreads();                               // previous image is done with shared memory
+        for (int g = tid; g < G; g += kEncThreads) {
+            float4 v = (g == tid) ? gb : gtb[g];
+            s_box[g] = v;
+            s_area[g] = (v.w - v.y) * (v.z - v.x);
+            s_best[g] = 0ull;
         }
+        const int bn = b + gridDim.y;
+        int Gn = 0;
+        float4 gbn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bn < p.B) {
+            Gn = p.gt_counts[bn];
+            Gn = Gn < 0 ? 0 : (Gn > p.Gmax ? p.Gmax : Gn);
+            if (tid < Gn) gbn = p.gt_boxes[(size_t)bn * p.Gmax + tid];
+        }
+        __syncthreads();
 
-        // ---- IoU sweep.  best/bestk: per-anchor running max and FIRST argmax over GT
-        // (strict '>' on an ascending GT list == tf.argmax first occurrence).
+        // ---- IoU sweep.  best/bestg: per-anchor running max and FIRST argmax over GT (strict
+        // '>' over ascending g == tf.argmax first occurrence).  32 GT boxes are culled against
+        // this warp's extent at once (one per lane, ballot); a pair can only have a positive
+        // intersection if the GT overlaps the union extent (float subtraction is sign exact),
+        // every skipped pair contributes exactly 0.
         float best[APT];
-        int bestk[APT];
+        int bestg[APT];
 #pragma unroll
-        for (int j = 0; j < APT; ++j) { best[j] = 0.f; bestk[j] = -1; }
+        for (int j = 0; j < APT; ++j) { best[j] = 0.f; bestg[j] = -1; }
 
-        for (int k = 0; k < ncull; ++k) {
-            const float4 g = s_box[k];
-            // warp-uniform cull against this warp's extent
-            if (!((fminf(g.z, wy1) > fmaxf(g.x, wy0)) && (fminf(g.w, wx1) > fmaxf(g.y, wx0)))) continue;
-            const float ga = s_area[k];
-            unsigned mybits = 0u;
-            unsigned myj = 0u;
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            bool touch = false;
+            if (g0 + lane < G) {
+                float4 t = s_box[g0 + lane];
+                touch = (fminf(t.z, wy1) > fmaxf(t.x, wy0)) && (fminf(t.w, wx1) > fmaxf(t.y, wx0));
+            }
+            unsigned todo = __ballot_sync(full, touch);
+            while (todo) {
+                const int g = g0 + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float4 t = s_box[g];
+                const float ga = s_area[g];
+                unsigned bits[APT];
 #pragma unroll
-            for (int j = 0; j < APT; ++j) {
-                float h = fminf(g.z, a[j].z) - fmaxf(g.x, a[j].x);
-                float w = fminf(g.w, a[j].w) - fmaxf(g.y, a[j].y);
-                if (h > 0.f && w > 0.f) {
+                for (int j = 0; j < APT; ++j) {
+                    // branch-free, exactly the reference's op order (ssd_common.py:34-47)
+                    float h = fmaxf(fminf(t.z, a[j].z) - fmaxf(t.x, a[j].x), 0.f);
+                    float w = fmaxf(fminf(t.w, a[j].w) - fmaxf(t.y, a[j].y), 0.f);
                     float inter = h * w;
                     float uni = (ga + area[j]) - inter;
                     float iou = (uni == 0.f) ? 0.f : inter / uni;
-                    if (iou > best[j]) { best[j] = iou; bestk[j] = k; }
-                    unsigned bits = __float_as_uint(iou);
-                    if (bits > mybits) { mybits = bits; myj = (unsigned)j; }
+                    if (iou > best[j]) { best[j] = iou; bestg[j] = g; }
+                    bits[j] = __float_as_uint(iou);
                 }
-            }
-            // per-GT (max, lowest anchor index): IoU >= 0 so float bits order as integers
-            unsigned m = __reduce_max_sync(full, mybits);
-            if (m != 0u) {
-                unsigned cand = (mybits == m) ? (myj * 32u + (unsigned)lane) : 0xffffffffu;
-                unsigned first = __reduce_min_sync(full, cand);
-                if (lane == 0) {
-                    u64 key = ((u64)m << 32) | (u64)(0xffffffffu - ((unsigned)warp_n0 + first));
-                    if (key > s_best[k]) atomicMax(&s_best[k], key);
+                // per-GT (max, lowest anchor index): IoU >= 0 so float bits order as integers
+                unsigned mybits = bits[0];
+#pragma unroll
+                for (int j = 1; j < APT; ++j) mybits = max(mybits, bits[j]);
+                const unsigned m = __reduce_max_sync(full, mybits);
+                if (m != 0u) {
+                    unsigned cand = 0xffffffffu;
+#pragma unroll
+                    for (int j = APT - 1; j >= 0; --j)
+                        if (bits[j] == m) cand = (unsigned)(j * 32 + lane);
+                    const unsigned first = __reduce_min_sync(full, cand);
+                    if (lane == 0) {
+                        u64 key = ((u64)m << 32) | (u64)(0xffffffffu - ((unsigned)warp_n0 + first));
+                        if (key > s_best[g]) atomicMax(&s_best[g], key);
+                    }
                 }
             }
         }
         __syncthreads();
 
-        for (int k = tid; k < ncull; k += kEncThreads) {
-            u64 v = s_best[k];
-            if (v != 0ull) atomicMax(p.ws_keys + (size_t)b * p.Gmax + s_gid[k], v);
+        for (int g = tid; g < G; g += kEncThreads) {
+            u64 v = s_best[g];
+            if (v != 0ull) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
         }
 
         // ---- label + encode + store (forced anchors are rewritten by match_force_kernel)
@@ -207,8 +189,7 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             int n = warp_n0 + j * 32 + lane;
             if (n >= p.N) continue;
             float mv = best[j];
-            int kb = bestk[j];
-            int a2g = (kb >= 0) ? s_gid[kb] : 0;
+            int a2g = bestg[j] < 0 ? 0 : bestg[j];
             bool less = mv < p.low;
             bool between = (mv < p.high) && (mv >= p.low);
             bool neg = p.ignore_between ? less : between;
@@ -218,9 +199,8 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             long long label = 0;
             float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (mi >= 0) {
-                float4 gb = (kb >= 0) ? s_box[kb] : gtb[0];
                 label = p.gt_labels[(size_t)b * p.Gmax + a2g];
-                loc = encode_loc(gb, p.enc[n], p);
+                loc = encode_loc(s_box[a2g], p.enc[n], p);
                 if (!p.gt_max_first) atomicOr(p.ws_claimed + (size_t)b * p.Gmax + a2g, 1u);
             } else if (mi < -1) {
                 label = -1;
@@ -232,6 +212,9 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             if (p.out_matched) p.out_matched[o] = mi;
             if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
         }
+        b = bn;
+        G = Gn;
+        gb = gbn;
     }
 }
 
@@ -255,25 +238,29 @@ match_force_kernel(const __grid_constant__ EncodeParams p) {
         p.ws_claimed[o] = 0u;
     }
     __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        if (s_cl[g]) continue;                    // gt_max_first=False: GT already has an anchor
-        const int n = s_n[g];
-        bool first = true;
-        for (int g2 = 0; g2 < g; ++g2)
-            if (s_n[g2] == n && !s_cl[g2]) { first = false; break; }
+    for (int g0 = 0; g0 < G; g0 += blockDim.x) {
+        const int g = g0 + threadIdx.x;
+        const bool act = g < G;
+        const int n = act ? s_n[g] : -1;
+        // uniform trip count (no early exit): lanes must stay converged for the body below
+        bool first = act && !s_cl[act ? g : 0];   // gt_max_first=False: a GT that already owns an anchor forces nothing
+        const int lim = min(G, g0 + (int)blockDim.x);
+        for (int g2 = 0; g2 < lim; ++g2) first = first && !(g2 < g && s_n[g2] == n && !s_cl[g2]);
         if (!first) continue;
         const float4 gb = p.gt_boxes[(size_t)b * p.Gmax + g];
         const float4 a = p.cor[n];
+        const float4 e = p.enc[n];
+        const bool in = p.inside[n] != 0;
+        const long long label = p.gt_labels[(size_t)b * p.Gmax + g];
         float h = fmaxf(fminf(gb.z, a.z) - fmaxf(gb.x, a.x), 0.f);
         float w = fmaxf(fminf(gb.w, a.w) - fmaxf(gb.y, a.y), 0.f);
         float inter = h * w;
         float uni = ((gb.w - gb.y) * (gb.z - gb.x) + (a.w - a.y) * (a.z - a.x)) - inter;
         float iou = (uni == 0.f) ? 0.f : inter / uni;
-        float ov = iou * (p.inside[n] ? 1.f : 0.f);
-        long long label = p.gt_labels[(size_t)b * p.Gmax + g];
+        float ov = iou * (in ? 1.f : 0.f);
         size_t o = (size_t)b * p.N + n;
         p.out_labels[o] = label;
-        p.out_loc[o] = encode_loc(gb, p.enc[n], p);
+        p.out_loc[o] = encode_loc(gb, e, p);
         p.out_scores[o] = ov;
         if (p.out_matched) p.out_matched[o] = g;
         if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
@@ -316,6 +303,7 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
                  RONK_EINVAL, "ronk_match_encode: gt_boxes/out_loc must be 16-byte aligned, ws 8-byte aligned");
     EncodeParams p;
     p.cor = (const float4*)h->d_cor;
+    p.mcor = (const float4*)h->d_mcor;
     p.enc = (const float4*)h->d_enc;
     p.inside = h->d_inside;
     p.N = h->tab.N;
@@ -346,7 +334,7 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     if (ipc < 1) ipc = 1;
     int Q = (B + ipc - 1) / ipc;
     if (Q > 65535) Q = 65535;
-    size_t smem = (size_t)p.gcap * (16 + 8 + 4 + 4);
+    size_t smem = (size_t)p.gcap * (16 + 8 + 4);
     cudaStream_t st = (cudaStream_t)stream;
     match_encode_kernel<kEncApt><<<dim3(tiles, Q), kEncThreads, smem, st>>>(p);
     RONK_LAUNCHED();
