@@ -78,6 +78,36 @@ anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ bord
                  : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 }
 
+cudaError_t finish_compaction(ronk_anchors* h) {
+    const int N = h->tab.N;
+    std::vector<uint8_t> in(N);
+    std::vector<float> cor((size_t)N * 4);
+    cudaError_t e = cudaMemcpy(in.data(), h->d_inside, (size_t)N, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cor.data(), h->d_cor, (size_t)N * 16, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    std::vector<int> idx, cidx(N);
+    std::vector<float> ccor;
+    idx.reserve(N);
+    for (int n = 0; n < N; ++n) {
+        if (in[n]) {
+            cidx[n] = (int)idx.size();
+            idx.push_back(n);
+            ccor.insert(ccor.end(), cor.begin() + (size_t)n * 4, cor.begin() + (size_t)n * 4 + 4);
+        } else {
+            cidx[n] = -1;
+        }
+    }
+    h->n_inside = (int)idx.size();
+    const size_t nin = idx.size() ? idx.size() : 1;
+    e = cudaMalloc(&h->d_inside_idx, nin * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_cidx, (size_t)N * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_ccor, nin * 16);
+    if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_inside_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_cidx, cidx.data(), (size_t)N * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_ccor, ccor.data(), ccor.size() * 4, cudaMemcpyHostToDevice);
+    return e;
+}
+
 }  // namespace ronk
 
 using namespace ronk;
@@ -120,6 +150,7 @@ extern "C" int ronk_anchors_create_flat(int img_h, int img_w, int N, const float
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = finish_compaction(h);
     if (d_border) cudaFree(d_border);
     if (e != cudaSuccess) {
         int r = cuda_fail(e, "ronk_anchors_create_flat");
@@ -234,6 +265,7 @@ extern "C" int ronk_anchors_create(int kind, int img_h, int img_w, int num_layer
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();   // creation only; compute calls never sync
+    if (e == cudaSuccess) e = finish_compaction(h);
     delete p;
     if (e != cudaSuccess) {
         int r = cuda_fail(e, "ronk_anchors_create");
@@ -251,6 +283,9 @@ extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
     if (h->d_cor) cudaFree(h->d_cor);
     if (h->d_inside) cudaFree(h->d_inside);
     if (h->d_mcor) cudaFree(h->d_mcor);
+    if (h->d_inside_idx) cudaFree(h->d_inside_idx);
+    if (h->d_cidx) cudaFree(h->d_cidx);
+    if (h->d_ccor) cudaFree(h->d_ccor);
     delete h;
 }
 

@@ -1,34 +1,45 @@
-// K1: fused all-layer GT->anchor matching + target encoding.
+// K1: fused all-layer GT->anchor matching + target encoding, ONE launch per batch.
 //
 // Reference: nets/ssd_common.py:27-47 (iou_matrix), :49-75 (do_dual_max_match), :77-147
 // (tf_ssd_bboxes_encode_layer), nets/ron_vgg_320.py:686,708 (objectness label).
 // Spec: SURVEY.md Appendix A.3/A.4.  Results are bit-exact against oracle/ron_oracle.py.
 //
-// Two launches per batch:
-//   match_encode_kernel  one CTA = one tile of consecutive anchors (kept in registers) x a
-//     group of images.  Per image the CTA culls the GT list against the tile's bounding box
-//     (order preserving, so "first GT wins" ties need no extra compare), evaluates IoU only
-//     where the intersection is positive (everything else is exactly 0 in float32), keeps
-//     the per-anchor (max, first argmax) in registers, reduces the per-GT (max, lowest
-//     anchor) as a packed u64 with REDUX + shared/global atomicMax, then labels, encodes and
-//     writes labels/loc/scores fully coalesced.  No [G,N] matrix ever exists.
-//   match_force_kernel   per image: reads the per-GT best anchors, applies "lowest GT index
-//     claims the anchor", rewrites those (<= G) anchors, and re-zeroes the workspace.
+// Work item = (tile of 256 consecutive INSIDE anchors, image).  Anchors outside the border mask
+// have overlap exactly 0 with everything (ssd_common.py:118), so only the compacted inside
+// anchors (65 % for RON-320) ever enter the IoU sweep; a tile still owns the contiguous range of
+// flat anchor indices around its inside anchors and writes all of their outputs coalesced.
+// Per image the CTA
+//   1. stages the GT boxes in shared memory;
+//   2. sweeps: every warp holds 64 anchors in registers, culls 32 GT boxes at a time against the
+//      warp's bounding extent (ballot; order preserving, so "first GT wins" needs no extra
+//      compare; a culled pair has intersection <= 0, i.e. IoU exactly 0), evaluates IoU in the
+//      reference's exact op order two GT boxes per iteration, keeps the per-anchor
+//      (max, first argmax) in registers and the per-GT (max, lowest anchor) as a packed u64 in
+//      shared memory -- the REDUX + atomicMax path only runs when a lane can beat the current
+//      per-GT best;
+//   3. labels, encodes and stores labels / loc / scores for its flat anchor range;
+//   4. publishes its per-GT bests with one global atomicMax each and bumps the image's tile
+//      counter; the CTA that finishes an image LAST applies "lowest GT index claims the anchor"
+//      (tf.argmax of the one-hot mask, ssd_common.py:74-75), rewrites those (<= G) anchors and
+//      restores the workspace to zero.  No [G,N] matrix ever exists, no second launch.
 #include <math_constants.h>
 
 #include "common.cuh"
 
 namespace ronk {
 
-constexpr int kEncThreads = 256;
-constexpr int kEncApt = 2;   // anchors per thread
+constexpr int kEncThreads = 128;
+constexpr int kEncApt = 2;                              // anchors per thread
+constexpr int kEncTile = kEncThreads * kEncApt;         // inside anchors per CTA
 
 struct EncodeParams {
-    const float4* cor;
-    const float4* mcor;
-    const float4* enc;
-    const uint8_t* inside;
-    int N;
+    const float4* cor;        // [N]   corners of every anchor (force phase)
+    const float4* ccor;       // [Nin] corners of the inside anchors
+    const int* inside_idx;    // [Nin] flat index of the inside anchors
+    const int* cidx;          // [N]   compact index or -1
+    const float4* enc;        // [N]   (cy, cx, h', w')
+    const uint8_t* inside;    // [N]
+    int N, Nin;
     const float4* gt_boxes;
     const long long* gt_labels;
     const int* gt_counts;
@@ -41,8 +52,9 @@ struct EncodeParams {
     float* out_scores;
     int* out_matched;
     int* out_obj;
-    u64* ws_keys;
-    unsigned* ws_claimed;
+    u64* ws_keys;             // [B*Gmax] per-GT (iou bits << 32 | ~compact anchor), zero between calls
+    unsigned* ws_claimed;     // [B*Gmax] gt_max_first=False bookkeeping, zero between calls
+    unsigned* ws_count;       // [B] tiles finished per image, zero between calls
 };
 
 // nets/ssd_common.py:130-144: (cx, cy, w, h) ordering, two true divisions per term.
@@ -59,29 +71,84 @@ __device__ __forceinline__ float4 encode_loc(float4 gb, float4 e, const EncodePa
     return make_float4(t_cx, t_cy, t_w, t_h);
 }
 
+// branch-free IoU in exactly the reference's op order (ssd_common.py:34-47)
+__device__ __forceinline__ float iou_ref(float4 t, float ga, float4 a, float aa) {
+    float h = fmaxf(fminf(t.z, a.z) - fmaxf(t.x, a.x), 0.f);
+    float w = fmaxf(fminf(t.w, a.w) - fmaxf(t.y, a.y), 0.f);
+    float inter = h * w;
+    float uni = (ga + aa) - inter;
+    return div_overlap(inter, uni);          // where(union == 0, 0, inter / union): union == 0 implies inter == 0
+}
+
+// Per image, run by the CTA that finished the image last: g2a[g] = decoded per-GT best anchor
+// (all-zero row -> anchor 0); the lowest GT index that claims an anchor wins; score =
+// overlap[g, n].  Also restores the workspace to zero for the next call.
+__device__ void force_image(const EncodeParams& p, int b, int G, int* s_n, int* s_cl) {
+    const int tid = threadIdx.x;
+    for (int g = tid; g < p.Gmax; g += kEncThreads) {
+        size_t o = (size_t)b * p.Gmax + g;
+        u64 key = __ldcg(p.ws_keys + o);
+        int n = 0;
+        if (key) n = p.inside_idx[0xffffffffu - (unsigned)(key & 0xffffffffull)];
+        s_n[g] = n;
+        s_cl[g] = p.gt_max_first ? 0 : (int)__ldcg(p.ws_claimed + o);
+        if (key) p.ws_keys[o] = 0ull;
+        if (!p.gt_max_first) p.ws_claimed[o] = 0u;
+    }
+    if (tid == 0) p.ws_count[b] = 0u;
+    __syncthreads();
+    for (int g0 = 0; g0 < G; g0 += kEncThreads) {
+        const int g = g0 + tid;
+        const bool act = g < G;
+        const int n = act ? s_n[g] : -1;
+        bool first = act && !s_cl[act ? g : 0];   // gt_max_first=False: a GT that already owns an anchor forces nothing
+        const int lim = min(G, g0 + kEncThreads);
+        for (int g2 = 0; g2 < lim; ++g2) first = first && !(g2 < g && s_n[g2] == n && !s_cl[g2]);
+        if (!first) continue;
+        const float4 gb = p.gt_boxes[(size_t)b * p.Gmax + g];
+        const float4 a = p.cor[n];
+        const float4 e = p.enc[n];
+        const bool in = p.inside[n] != 0;
+        const long long label = p.gt_labels[(size_t)b * p.Gmax + g];
+        float iou = iou_ref(gb, (gb.w - gb.y) * (gb.z - gb.x), a, (a.w - a.y) * (a.z - a.x));
+        float ov = iou * (in ? 1.f : 0.f);
+        size_t o = (size_t)b * p.N + n;
+        p.out_labels[o] = label;
+        p.out_loc[o] = encode_loc(gb, e, p);
+        p.out_scores[o] = ov;
+        if (p.out_matched) p.out_matched[o] = g;
+        if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
+    }
+}
+
 template <int APT>
-__global__ void __launch_bounds__(kEncThreads, 4)
+__global__ void __launch_bounds__(kEncThreads, 8)
 match_encode_kernel(const __grid_constant__ EncodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     float4* s_box = reinterpret_cast<float4*>(smem);              // [gcap] GT corners
-    u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [gcap] per-GT (iou bits, ~anchor) of this tile
+    u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [gcap] per-GT (iou bits, ~compact anchor) of this tile
     float* s_area = reinterpret_cast<float*>(s_best + p.gcap);    // [gcap]
+    __shared__ float s_mv[kEncThreads * APT];                     // per-anchor max overlap of this tile
+    __shared__ int s_mg[kEncThreads * APT];                       // per-anchor first argmax (-1: none)
+    __shared__ int s_last;
 
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int warp_n0 = blockIdx.x * (kEncThreads * APT) + warp * (32 * APT);
+    const int c0 = blockIdx.x * (kEncThreads * APT);
+    const int warp_c0 = c0 + warp * (32 * APT);
+    // flat anchor range whose outputs this tile writes: from its first inside anchor up to the next tile's
+    const int n_lo = (blockIdx.x == 0) ? 0 : p.inside_idx[c0];
+    const int n_hi = (c0 + kEncThreads * APT >= p.Nin) ? p.N : p.inside_idx[c0 + kEncThreads * APT];
 
-    // ---- this thread's anchors: corners + area in registers for the whole image loop.  The
-    // match table already holds an empty box (+inf,+inf,-inf,-inf) for anchors outside the
-    // border mask: their overlap with everything is exactly 0 (ssd_common.py:118).
+    // ---- this thread's anchors: corners + area in registers for the whole image loop
     float4 a[APT];
     float area[APT];
     float wy0 = CUDART_INF_F, wx0 = CUDART_INF_F, wy1 = -CUDART_INF_F, wx1 = -CUDART_INF_F;
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
-        int n = warp_n0 + j * 32 + lane;
-        a[j] = (n < p.N) ? p.mcor[n] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-        const bool in = a[j].x != CUDART_INF_F;          // false only for the empty box
+        int c = warp_c0 + j * 32 + lane;
+        const bool in = c < p.Nin;
+        a[j] = in ? p.ccor[c] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
         area[j] = in ? (a[j].w - a[j].y) * (a[j].z - a[j].x) : 0.f;
         wy0 = fminf(wy0, a[j].x);
         wx0 = fminf(wx0, a[j].y);
@@ -96,39 +163,21 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
         wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
     }
 
-    // software prefetch of the next image's GT boxes (one per thread; G > 256 reads the rest late)
-    int b = blockIdx.y;
-    int G = 0;
-    float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < p.B) {
-        G = p.gt_counts[b];
-        G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
-        if (tid < G) gb = p.gt_boxes[(size_t)b * p.Gmax + tid];
-    }
-    for (; b < p.B;) {
+    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
         const float4* gtb = p.gt_boxes + (size_t)b * p.Gmax;
+        int G = p.gt_counts[b];
+        G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
         __syncthreads();                               // previous image is done with shared memory
         for (int g = tid; g < G; g += kEncThreads) {
-            float4 v = (g == tid) ? gb : gtb[g];
+            float4 v = gtb[g];
             s_box[g] = v;
             s_area[g] = (v.w - v.y) * (v.z - v.x);
             s_best[g] = 0ull;
         }
-        const int bn = b + gridDim.y;
-        int Gn = 0;
-        float4 gbn = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bn < p.B) {
-            Gn = p.gt_counts[bn];
-            Gn = Gn < 0 ? 0 : (Gn > p.Gmax ? p.Gmax : Gn);
-            if (tid < Gn) gbn = p.gt_boxes[(size_t)bn * p.Gmax + tid];
-        }
         __syncthreads();
 
         // ---- IoU sweep.  best/bestg: per-anchor running max and FIRST argmax over GT (strict
-        // '>' over ascending g == tf.argmax first occurrence).  32 GT boxes are culled against
-        // this warp's extent at once (one per lane, ballot); a pair can only have a positive
-        // intersection if the GT overlaps the union extent (float subtraction is sign exact),
-        // every skipped pair contributes exactly 0.
+        // '>' over ascending g == tf.argmax first occurrence).
         float best[APT];
         int bestg[APT];
 #pragma unroll
@@ -142,39 +191,61 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             }
             unsigned todo = __ballot_sync(full, touch);
             while (todo) {
-                const int g = g0 + __ffs(todo) - 1;
+                // two GT boxes per iteration (the second repeats the first when only one is left:
+                // max / first-argmax / atomicMax are idempotent) for instruction-level parallelism
+                int gq[2];
+                gq[0] = g0 + __ffs(todo) - 1;
                 todo &= todo - 1;
-                const float4 t = s_box[g];
-                const float ga = s_area[g];
-                unsigned bits[APT];
+                gq[1] = todo ? g0 + __ffs(todo) - 1 : gq[0];
+                todo &= todo - 1;
+                float4 t[2];
+                float ga[2];
+                unsigned cur[2];
 #pragma unroll
-                for (int j = 0; j < APT; ++j) {
-                    // branch-free, exactly the reference's op order (ssd_common.py:34-47)
-                    float h = fmaxf(fminf(t.z, a[j].z) - fmaxf(t.x, a[j].x), 0.f);
-                    float w = fmaxf(fminf(t.w, a[j].w) - fmaxf(t.y, a[j].y), 0.f);
-                    float inter = h * w;
-                    float uni = (ga + area[j]) - inter;
-                    float iou = (uni == 0.f) ? 0.f : inter / uni;
-                    if (iou > best[j]) { best[j] = iou; bestg[j] = g; }
-                    bits[j] = __float_as_uint(iou);
+                for (int q = 0; q < 2; ++q) {
+                    t[q] = s_box[gq[q]];
+                    ga[q] = s_area[gq[q]];
+                    cur[q] = (unsigned)(s_best[gq[q]] >> 32);       // stale values are only lower: a safe filter
                 }
-                // per-GT (max, lowest anchor index): IoU >= 0 so float bits order as integers
-                unsigned mybits = bits[0];
+                unsigned bits[2][APT];
 #pragma unroll
-                for (int j = 1; j < APT; ++j) mybits = max(mybits, bits[j]);
-                const unsigned m = __reduce_max_sync(full, mybits);
-                if (m != 0u) {
-                    unsigned cand = 0xffffffffu;
+                for (int q = 0; q < 2; ++q) {
 #pragma unroll
-                    for (int j = APT - 1; j >= 0; --j)
-                        if (bits[j] == m) cand = (unsigned)(j * 32 + lane);
-                    const unsigned first = __reduce_min_sync(full, cand);
-                    if (lane == 0) {
-                        u64 key = ((u64)m << 32) | (u64)(0xffffffffu - ((unsigned)warp_n0 + first));
-                        if (key > s_best[g]) atomicMax(&s_best[g], key);
+                    for (int j = 0; j < APT; ++j) {
+                        float iou = iou_ref(t[q], ga[q], a[j], area[j]);
+                        bits[q][j] = __float_as_uint(iou);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    unsigned mybits = 0u;
+#pragma unroll
+                    for (int j = 0; j < APT; ++j) {
+                        float iou = __uint_as_float(bits[q][j]);
+                        if (iou > best[j]) { best[j] = iou; bestg[j] = gq[q]; }
+                        mybits = max(mybits, bits[q][j]);
+                    }
+                    // per-GT (max, lowest anchor index): IoU >= 0 so float bits order as integers.
+                    // Only when some lane reaches the GT's current best does the warp reduce.
+                    if (__any_sync(full, mybits != 0u && mybits >= cur[q])) {
+                        const unsigned m = __reduce_max_sync(full, mybits);
+                        unsigned cand = 0xffffffffu;
+#pragma unroll
+                        for (int j = APT - 1; j >= 0; --j)
+                            if (bits[q][j] == m) cand = (unsigned)(j * 32 + lane);
+                        const unsigned first = __reduce_min_sync(full, cand);
+                        if (lane == 0) {
+                            u64 key = ((u64)m << 32) | (u64)(0xffffffffu - ((unsigned)warp_c0 + first));
+                            atomicMax(&s_best[gq[q]], key);
+                        }
                     }
                 }
             }
+        }
+#pragma unroll
+        for (int j = 0; j < APT; ++j) {
+            s_mv[warp * (32 * APT) + j * 32 + lane] = best[j];
+            s_mg[warp * (32 * APT) + j * 32 + lane] = bestg[j];
         }
         __syncthreads();
 
@@ -183,13 +254,17 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             if (v != 0ull) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
         }
 
-        // ---- label + encode + store (forced anchors are rewritten by match_force_kernel)
-#pragma unroll
-        for (int j = 0; j < APT; ++j) {
-            int n = warp_n0 + j * 32 + lane;
-            if (n >= p.N) continue;
-            float mv = best[j];
-            int a2g = bestg[j] < 0 ? 0 : bestg[j];
+        // ---- label + encode + store the tile's flat anchor range (forced anchors are rewritten
+        // by the CTA that finishes the image last)
+        for (int n = n_lo + tid; n < n_hi; n += kEncThreads) {
+            const int c = p.cidx[n];
+            float mv = 0.f;
+            int a2g = 0;
+            if (c >= 0) {
+                mv = s_mv[c - c0];
+                int g = s_mg[c - c0];
+                a2g = g < 0 ? 0 : g;
+            }
             bool less = mv < p.low;
             bool between = (mv < p.high) && (mv >= p.low);
             bool neg = p.ignore_between ? less : between;
@@ -212,58 +287,20 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             if (p.out_matched) p.out_matched[o] = mi;
             if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
         }
-        b = bn;
-        G = Gn;
-        gb = gbn;
-    }
-}
 
-// Per image: g2a[g] = decoded per-GT best anchor (all-zero row -> anchor 0); the lowest GT
-// index that claims an anchor wins (tf.argmax of the one-hot mask, ssd_common.py:74-75);
-// score = overlap[g, n].  Also restores the workspace to zero for the next call.
-__global__ void __launch_bounds__(128)
-match_force_kernel(const __grid_constant__ EncodeParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    int* s_n = reinterpret_cast<int*>(smem);
-    int* s_cl = s_n + p.Gmax;
-    const int b = blockIdx.x;
-    int G = p.gt_counts[b];
-    G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
-    for (int g = threadIdx.x; g < p.Gmax; g += blockDim.x) {
-        size_t o = (size_t)b * p.Gmax + g;
-        u64 key = p.ws_keys[o];
-        s_n[g] = key ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : 0;
-        s_cl[g] = p.gt_max_first ? 0 : (int)p.ws_claimed[o];
-        p.ws_keys[o] = 0ull;
-        p.ws_claimed[o] = 0u;
-    }
-    __syncthreads();
-    for (int g0 = 0; g0 < G; g0 += blockDim.x) {
-        const int g = g0 + threadIdx.x;
-        const bool act = g < G;
-        const int n = act ? s_n[g] : -1;
-        // uniform trip count (no early exit): lanes must stay converged for the body below
-        bool first = act && !s_cl[act ? g : 0];   // gt_max_first=False: a GT that already owns an anchor forces nothing
-        const int lim = min(G, g0 + (int)blockDim.x);
-        for (int g2 = 0; g2 < lim; ++g2) first = first && !(g2 < g && s_n[g2] == n && !s_cl[g2]);
-        if (!first) continue;
-        const float4 gb = p.gt_boxes[(size_t)b * p.Gmax + g];
-        const float4 a = p.cor[n];
-        const float4 e = p.enc[n];
-        const bool in = p.inside[n] != 0;
-        const long long label = p.gt_labels[(size_t)b * p.Gmax + g];
-        float h = fmaxf(fminf(gb.z, a.z) - fmaxf(gb.x, a.x), 0.f);
-        float w = fmaxf(fminf(gb.w, a.w) - fmaxf(gb.y, a.y), 0.f);
-        float inter = h * w;
-        float uni = ((gb.w - gb.y) * (gb.z - gb.x) + (a.w - a.y) * (a.z - a.x)) - inter;
-        float iou = (uni == 0.f) ? 0.f : inter / uni;
-        float ov = iou * (in ? 1.f : 0.f);
-        size_t o = (size_t)b * p.N + n;
-        p.out_labels[o] = label;
-        p.out_loc[o] = encode_loc(gb, e, p);
-        p.out_scores[o] = ov;
-        if (p.out_matched) p.out_matched[o] = g;
-        if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
+        // ---- publish; the last tile of the image applies the per-GT forcing
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned prev = atomicAdd(p.ws_count + b, 1u);
+            s_last = (prev == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            // s_best (8 B per GT slot) is free now: reuse it as two int arrays
+            force_image(p, b, G, reinterpret_cast<int*>(s_best), reinterpret_cast<int*>(s_best) + p.gcap);
+        }
     }
 }
 
@@ -278,7 +315,7 @@ using namespace ronk;
 
 extern "C" size_t ronk_encode_workspace_bytes(int B, int Gmax) {
     if (B < 1 || Gmax < 1) return 0;
-    return (size_t)B * Gmax * (sizeof(u64) + sizeof(unsigned));
+    return (size_t)B * Gmax * (sizeof(u64) + sizeof(unsigned)) + (size_t)B * sizeof(unsigned);
 }
 
 extern "C" int ronk_encode_workspace_init(void* ws, int B, int Gmax, void* stream) {
@@ -303,10 +340,13 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
                  RONK_EINVAL, "ronk_match_encode: gt_boxes/out_loc must be 16-byte aligned, ws 8-byte aligned");
     EncodeParams p;
     p.cor = (const float4*)h->d_cor;
-    p.mcor = (const float4*)h->d_mcor;
+    p.ccor = (const float4*)h->d_ccor;
+    p.inside_idx = h->d_inside_idx;
+    p.cidx = h->d_cidx;
     p.enc = (const float4*)h->d_enc;
     p.inside = h->d_inside;
     p.N = h->tab.N;
+    p.Nin = h->n_inside;
     p.gt_boxes = (const float4*)gt_boxes;
     p.gt_labels = (const long long*)gt_labels;
     p.gt_counts = gt_counts;
@@ -325,11 +365,13 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     p.out_obj = out_objness;
     p.ws_keys = (u64*)ws;
     p.ws_claimed = (unsigned*)((u64*)ws + (size_t)B * Gmax);
+    p.ws_count = p.ws_claimed + (size_t)B * Gmax;
 
-    const int tile = kEncThreads * kEncApt;
-    const int tiles = (p.N + tile - 1) / tile;
-    // image groups: aim at ~8 resident CTAs per SM, every CTA loops over >= 1 image
-    long long want = (long long)h->num_sms * 8;
+    int tiles = (p.Nin + kEncTile - 1) / kEncTile;
+    if (tiles < 1) tiles = 1;
+    // image groups: every CTA keeps its anchors in registers and loops over images; aim at a few
+    // waves of resident CTAs so the hardware scheduler balances the uneven (G-dependent) work
+    long long want = (long long)h->num_sms * 8 * 4;
     int ipc = (int)(((long long)B * tiles) / want);
     if (ipc < 1) ipc = 1;
     int Q = (B + ipc - 1) / ipc;
@@ -337,8 +379,6 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     size_t smem = (size_t)p.gcap * (16 + 8 + 4);
     cudaStream_t st = (cudaStream_t)stream;
     match_encode_kernel<kEncApt><<<dim3(tiles, Q), kEncThreads, smem, st>>>(p);
-    RONK_LAUNCHED();
-    match_force_kernel<<<B, 128, (size_t)Gmax * 8, st>>>(p);
     RONK_LAUNCHED();
     return RONK_OK;
 }

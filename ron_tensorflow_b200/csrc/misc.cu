@@ -26,7 +26,7 @@ pairwise_kernel(const float4* __restrict__ a, int G, const float4* __restrict__ 
     float r = inter;
     if (mode == 1) {
         float uni = ((x.w - x.y) * (x.z - x.x) + (y.w - y.y) * (y.z - y.x)) - inter;
-        r = (uni == 0.f) ? 0.f : inter / uni;
+        r = div_overlap(inter, uni);
     }
     out[(size_t)g * N + n] = r;
 }

@@ -31,6 +31,10 @@ struct NmsParams {
 };
 
 // does kept box i suppress candidate j?  (j is the later one: tf_extended/bboxes.py:195-211)
+// overlap = inner / den rounded to float32, suppressed iff !(overlap < thr).  The division is
+// only executed when inner is within 1e-6 (relative) of thr * den: outside that band the
+// rounded quotient cannot land on the other side of thr (float32 rounding moves it by at most
+// 6e-8 relative and is monotonic), so the sign of inner - thr * den decides.
 __device__ __forceinline__ bool suppresses(float4 bj, float vj, float4 bi, float vi, int mode, float thr,
                                            bool zero_suppresses) {
     float h = fminf(bj.z, bi.z) - fmaxf(bj.x, bi.x);
@@ -38,8 +42,11 @@ __device__ __forceinline__ bool suppresses(float4 bj, float vj, float4 bi, float
     if (h > 0.f && w > 0.f) {
         float inner = h * w;
         float den = (mode == RONK_NMS_UNION) ? ((vj - inner) + vi) : fminf(vj, vi);
-        float o = (den > 0.f) ? inner / den : 0.f;
-        return !(o < thr);
+        if (!(den > 0.f)) return zero_suppresses;          // safe_divide: overlap is 0
+        float t = thr * den;
+        float d = inner - t;
+        if (fabsf(d) > t * 1e-6f) return d > 0.f;
+        return !(inner / den < thr);
     }
     return zero_suppresses;   // overlap is exactly 0: suppressed only when !(0 < thr)
 }
@@ -73,30 +80,34 @@ nms_kernel(const __grid_constant__ NmsParams p) {
             score = p.scores[in0 + pos];
         }
         const float vol = (box.w - box.y) * (box.z - box.x);
-        bool alive = valid;
-        for (int i = 0; i < count; ++i) {
-            float4 kb = s_kbox[i];
-            float kv = s_kvol[i];
-            if (alive && suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp)) alive = false;
+        // 1. against everything kept by earlier chunks (broadcast reads; no loop-carried branch)
+        bool dead = !valid;
+        for (int i0 = 0; i0 < count; i0 += 8) {
+            const int lim = min(8, count - i0);
+#pragma unroll 4
+            for (int i = 0; i < lim; ++i) {
+                float4 kb = s_kbox[i0 + i];
+                float kv = s_kvol[i0 + i];
+                dead |= suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp);
+            }
+            if (__all_sync(full, dead)) break;
         }
+        // 2. inside the chunk: walk the survivors in order; each one that is still alive is kept
+        //    and kills the later lanes it overlaps
         s_cbox[lane] = box;
         s_cvol[lane] = vol;
         __syncwarp();
-        unsigned supp = 0u;   // earlier lanes of this chunk that would suppress this lane if kept
-        for (int i = 0; i < 31; ++i) {
-            float4 kb = s_cbox[i];
-            float kv = s_cvol[i];
-            if (i < lane && suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp)) supp |= 1u << i;
-        }
-        const unsigned alive_mask = __ballot_sync(full, alive);
+        unsigned alive_mask = __ballot_sync(full, !dead);
         unsigned kept = 0u;
         int room = p.M - count;
-        for (int l = 0; l < 32; ++l) {
-            unsigned sl = __shfl_sync(full, supp, l);
-            if (((alive_mask >> l) & 1u) && !(sl & kept) && room > 0) {
-                kept |= 1u << l;
-                --room;
-            }
+        while (alive_mask && room > 0) {
+            const int i = __ffs(alive_mask) - 1;
+            kept |= 1u << i;
+            --room;
+            float4 kb = s_cbox[i];
+            float kv = s_cvol[i];
+            if (lane > i && !dead) dead = suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp);
+            alive_mask = __ballot_sync(full, !dead) & ~((2u << i) - 1u);
         }
         if ((kept >> lane) & 1u) {
             int r = count + __popc(kept & ((1u << lane) - 1u));

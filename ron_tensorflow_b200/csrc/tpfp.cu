@@ -2,8 +2,14 @@
 //
 // Reference: tf_extended/bboxes.py:316-404 (bboxes_matching), :407-450 (bboxes_matching_batch),
 // :527-554 (bboxes_jaccard).  Spec: SURVEY.md Appendix A.8.  Bit-exact against the oracle.
-// The detection loop is inherently sequential (a GT can be matched once); lanes run over the
-// ground-truth boxes of the image, staged once per CTA in shared memory.
+//
+// The reference walks the detections one by one because a ground-truth box can be matched only
+// once.  Only that "already matched" bit is sequential: the jaccard arg-max of a detection does
+// not depend on the others.  So every lane takes one detection of a 32-wide chunk, scans the
+// image's ground truth (staged once per CTA in shared memory) for its first arg-max, and the
+// chunk is then resolved in one step: a detection sees its GT as "existing" if an earlier chunk
+// matched it (bitmask in shared memory) or an earlier lane of this chunk does (match_any +
+// lane mask).  M detections cost ceil(M/32) steps instead of M.
 #include "common.cuh"
 
 namespace ronk {
@@ -58,39 +64,46 @@ tpfp_kernel(const __grid_constant__ TpfpParams p) {
     const size_t seg = (size_t)b * CM + ci;
     if (lane == 0) p.out_n_gt[seg] = cnt;
 
-    for (int i = 0; i < p.M; ++i) {
-        const float4 r = p.det_boxes[seg * p.M + i];
+    for (int i0 = 0; i0 < p.M; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < p.M;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) r = p.det_boxes[seg * p.M + i];
         const float rarea = (r.z - r.x) * (r.w - r.y);
-        // jaccard vs every GT, masked by class; lane-local first argmax
-        float best = -1.f;
-        int bestg = 0x7fffffff;
-        for (int g = lane; g < p.Gmax; g += 32) {
-            float4 gb = s_gbox[g];
-            float h = fmaxf(fminf(gb.z, r.z) - fmaxf(gb.x, r.x), 0.f);
-            float w = fmaxf(fminf(gb.w, r.w) - fmaxf(gb.y, r.y), 0.f);
-            float inter = h * w;
-            float uni = (-inter + s_garea[g]) + rarea;
-            float jac = (uni > 0.f) ? inter / uni : 0.f;
-            jac = jac * ((s_glab[g] == label) ? 1.f : 0.f);
-            if (jac > best) { best = jac; bestg = g; }
+        // jaccard vs every GT, masked by class; first arg-max.  GT boxes of another class have
+        // jaccard * 0 = 0 and every jaccard is >= 0, so starting from (0, GT 0) and visiting only
+        // this class's boxes in ascending order with a strict '>' gives the same first arg-max.
+        float best = 0.f;
+        int idx = 0;
+        for (int g0 = 0; g0 < p.Gmax; g0 += 32) {
+            unsigned mine = __ballot_sync(full, g0 + lane < p.Gmax && s_glab[min(g0 + lane, p.Gmax - 1)] == label);
+            while (mine) {
+                const int g = g0 + __ffs(mine) - 1;
+                mine &= mine - 1;
+                float4 gb = s_gbox[g];
+                float h = fmaxf(fminf(gb.z, r.z) - fmaxf(gb.x, r.x), 0.f);
+                float w = fmaxf(fminf(gb.w, r.w) - fmaxf(gb.y, r.y), 0.f);
+                float inter = h * w;
+                float uni = (-inter + s_garea[g]) + rarea;
+                float jac = div_overlap(inter, uni);   // safe_divide: inter > 0 implies uni > 0
+                if (jac > best) { best = jac; idx = g; }
+            }
         }
-        // warp argmax, first occurrence: jaccard >= 0 so the bit pattern orders like the value
-        unsigned bits = (bestg == 0x7fffffff) ? 0u : __float_as_uint(best) + 1u;   // +1: lanes with no GT lose
-        unsigned m = __reduce_max_sync(full, bits);
-        unsigned cand = (bits == m && bestg != 0x7fffffff) ? (unsigned)bestg : 0xffffffffu;
-        const int idx = (int)__reduce_min_sync(full, cand);
-        const float jmax = __uint_as_float(m - 1u);
-        const bool is_match = jmax > p.thr;
-        const bool existing = (match[idx >> 5] >> (idx & 31)) & 1u;
+        const bool is_match = best > p.thr;
         const bool nd = !s_gdiff[idx];
+        const bool marks = valid && nd && is_match;            // this detection marks its GT (bboxes.py:377-380)
+        const unsigned markers = __ballot_sync(full, marks);
+        const unsigned same = __match_any_sync(full, idx);
+        const bool earlier = (same & markers & ((1u << lane) - 1u)) != 0u;
+        const bool existing = (((match[idx >> 5] >> (idx & 31)) & 1u) != 0u) || earlier;
         const bool tp = nd && is_match && !existing;
         const bool fp = nd && (existing || !is_match);
-        __syncwarp();
-        if (lane == 0) {
+        if (valid) {
             p.out_tp[seg * p.M + i] = tp ? 1 : 0;
             p.out_fp[seg * p.M + i] = fp ? 1 : 0;
-            if (nd && is_match) match[idx >> 5] |= 1u << (idx & 31);
         }
+        __syncwarp();
+        if (marks) atomicOr(&match[idx >> 5], 1u << (idx & 31));
         __syncwarp();
     }
 }
