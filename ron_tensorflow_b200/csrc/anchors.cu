@@ -98,6 +98,11 @@ cudaError_t finish_compaction(ronk_anchors* h) {
         }
     }
     h->n_inside = (int)idx.size();
+    h->anchors_nice = 1;
+    for (float v : ccor) {
+        float m = fabsf(v);
+        if (!(v == 0.f || (m >= 3.0517578125e-05f && m <= 32768.f))) h->anchors_nice = 0;
+    }
     const size_t nin = idx.size() ? idx.size() : 1;
     e = cudaMalloc(&h->d_inside_idx, nin * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cidx, (size_t)N * 4);

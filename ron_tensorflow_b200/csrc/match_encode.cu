@@ -4,33 +4,39 @@
 // (tf_ssd_bboxes_encode_layer), nets/ron_vgg_320.py:686,708 (objectness label).
 // Spec: SURVEY.md Appendix A.3/A.4.  Results are bit-exact against oracle/ron_oracle.py.
 //
-// Work item = (tile of 256 consecutive INSIDE anchors, image).  Anchors outside the border mask
+// Work item = (tile of consecutive INSIDE anchors, image).  Anchors outside the border mask
 // have overlap exactly 0 with everything (ssd_common.py:118), so only the compacted inside
 // anchors (65 % for RON-320) ever enter the IoU sweep; a tile still owns the contiguous range of
 // flat anchor indices around its inside anchors and writes all of their outputs coalesced.
+// A CTA has 4 warps = SETS anchor sets (64 anchors each, in registers) x SPLIT contiguous parts
+// of the image's GT list: (4,1) for large batches, (1,4) when the batch is too small to fill the
+// machine, so that the heaviest item (50 GT boxes that all touch the set) is cut in four.
 // Per image the CTA
 //   1. stages the GT boxes in shared memory;
-//   2. sweeps: every warp holds 64 anchors in registers, culls 32 GT boxes at a time against the
-//      warp's bounding extent (ballot; order preserving, so "first GT wins" needs no extra
-//      compare; a culled pair has intersection <= 0, i.e. IoU exactly 0), evaluates IoU in the
-//      reference's exact op order two GT boxes per iteration, keeps the per-anchor
-//      (max, first argmax) in registers and the per-GT (max, lowest anchor) as a packed u64 in
-//      shared memory -- the REDUX + atomicMax path only runs when a lane can beat the current
-//      per-GT best;
+//   2. sweeps: every warp culls 32 GT boxes at a time against its set's bounding extent (ballot;
+//      order preserving, so "first GT wins" needs no extra compare; a culled pair has
+//      intersection <= 0, i.e. IoU exactly 0), evaluates IoU in the reference's exact op order
+//      two GT boxes per iteration, keeps the per-anchor (max, first argmax) in registers and the
+//      per-GT (max, lowest anchor) as a packed u64 in shared memory -- the REDUX + atomicMax
+//      path only runs when a lane can reach the current per-GT best;
 //   3. labels, encodes and stores labels / loc / scores for its flat anchor range;
 //   4. publishes its per-GT bests with one global atomicMax each and bumps the image's tile
 //      counter; the CTA that finishes an image LAST applies "lowest GT index claims the anchor"
 //      (tf.argmax of the one-hot mask, ssd_common.py:74-75), rewrites those (<= G) anchors and
 //      restores the workspace to zero.  No [G,N] matrix ever exists, no second launch.
+// Tiles of the coarse layers (big anchors: every GT touches them) are the heaviest and come first
+// in the flat order; the grid is tile-major so they are dispatched first.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace ronk {
 
 constexpr int kEncThreads = 128;
-constexpr int kEncApt = 2;                              // anchors per thread
-constexpr int kEncTile = kEncThreads * kEncApt;         // inside anchors per CTA
+constexpr int kEncWarps = kEncThreads / 32;
+constexpr int kEncApt = 2;                              // anchors per lane
+constexpr int kEncSet = 32 * kEncApt;                   // anchors per warp-set
 
 struct EncodeParams {
     const float4* cor;        // [N]   corners of every anchor (force phase)
@@ -39,7 +45,7 @@ struct EncodeParams {
     const int* cidx;          // [N]   compact index or -1
     const float4* enc;        // [N]   (cy, cx, h', w')
     const uint8_t* inside;    // [N]
-    int N, Nin;
+    int N, Nin, tiles, anchors_nice;
     const float4* gt_boxes;
     const long long* gt_labels;
     const int* gt_counts;
@@ -71,13 +77,23 @@ __device__ __forceinline__ float4 encode_loc(float4 gb, float4 e, const EncodePa
     return make_float4(t_cx, t_cy, t_w, t_h);
 }
 
-// branch-free IoU in exactly the reference's op order (ssd_common.py:34-47)
+// branch-free IoU in exactly the reference's op order (ssd_common.py:34-47).
+// NICE: every coordinate is 0 or has a magnitude in [2^-15, 2^15] (checked per anchor handle and
+// per image), so the quotient takes the inline division sequence; otherwise IEEE div.rn.
+template <bool NICE>
 __device__ __forceinline__ float iou_ref(float4 t, float ga, float4 a, float aa) {
     float h = fmaxf(fminf(t.z, a.z) - fmaxf(t.x, a.x), 0.f);
     float w = fmaxf(fminf(t.w, a.w) - fmaxf(t.y, a.y), 0.f);
     float inter = h * w;
     float uni = (ga + aa) - inter;
-    return div_overlap(inter, uni);          // where(union == 0, 0, inter / union): union == 0 implies inter == 0
+    // where(union == 0, 0, inter / union); union == 0 implies inter == 0
+    return NICE ? div_overlap_nice(inter, uni) : div_overlap(inter, uni);
+}
+
+__device__ __forceinline__ bool nice_coord(float v) {
+    // 0, or 2^-15 <= |v| <= 2^15 (NaN / inf fail)
+    unsigned e = (__float_as_uint(v) >> 23) & 0xffu;
+    return v == 0.f || (e >= 127u - 15u && e <= 127u + 15u);
 }
 
 // Per image, run by the CTA that finished the image last: g2a[g] = decoded per-GT best anchor
@@ -110,7 +126,7 @@ __device__ void force_image(const EncodeParams& p, int b, int G, int* s_n, int* 
         const float4 e = p.enc[n];
         const bool in = p.inside[n] != 0;
         const long long label = p.gt_labels[(size_t)b * p.Gmax + g];
-        float iou = iou_ref(gb, (gb.w - gb.y) * (gb.z - gb.x), a, (a.w - a.y) * (a.z - a.x));
+        float iou = iou_ref<false>(gb, (gb.w - gb.y) * (gb.z - gb.x), a, (a.w - a.y) * (a.z - a.x));
         float ov = iou * (in ? 1.f : 0.f);
         size_t o = (size_t)b * p.N + n;
         p.out_labels[o] = label;
@@ -121,137 +137,160 @@ __device__ void force_image(const EncodeParams& p, int b, int G, int* s_n, int* 
     }
 }
 
-template <int APT>
-__global__ void __launch_bounds__(kEncThreads, 8)
+// IoU sweep of one warp over GT boxes [g_lo, g_hi).  best/bestg: per-anchor running max and
+// FIRST argmax over GT (strict '>' over ascending g == tf.argmax first occurrence).
+template <bool NICE>
+__device__ __forceinline__ void sweep(const float4* s_box, const float* s_area, u64* s_best, int g_lo, int g_hi,
+                                      const float4 (&a)[kEncApt], const float (&area)[kEncApt], float wy0, float wx0,
+                                      float wy1, float wx1, unsigned set_c0, float (&best)[kEncApt],
+                                      int (&bestg)[kEncApt]) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int g0 = g_lo; g0 < g_hi; g0 += 32) {
+        bool touch = false;
+        if (g0 + lane < g_hi) {
+            float4 t = s_box[g0 + lane];
+            touch = (fminf(t.z, wy1) > fmaxf(t.x, wy0)) && (fminf(t.w, wx1) > fmaxf(t.y, wx0));
+        }
+        unsigned todo = __ballot_sync(full, touch);
+        while (todo) {
+            // two GT boxes per iteration (the second repeats the first when only one is left:
+            // max / first-argmax / atomicMax are idempotent) for instruction-level parallelism
+            int gq[2];
+            gq[0] = g0 + __ffs(todo) - 1;
+            todo &= todo - 1;
+            gq[1] = todo ? g0 + __ffs(todo) - 1 : gq[0];
+            todo &= todo - 1;
+            float4 t[2];
+            float ga[2];
+            unsigned cur[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                t[q] = s_box[gq[q]];
+                ga[q] = s_area[gq[q]];
+                // stale values are only lower: a safe filter; >= 1 so that zero overlaps never pass
+                cur[q] = max((unsigned)(s_best[gq[q]] >> 32), 1u);
+            }
+            unsigned bits[2][kEncApt];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int j = 0; j < kEncApt; ++j)
+                    bits[q][j] = __float_as_uint(iou_ref<NICE>(t[q], ga[q], a[j], area[j]));
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                unsigned mybits = 0u;
+#pragma unroll
+                for (int j = 0; j < kEncApt; ++j) {
+                    float iou = __uint_as_float(bits[q][j]);
+                    if (iou > best[j]) { best[j] = iou; bestg[j] = gq[q]; }
+                    mybits = max(mybits, bits[q][j]);
+                }
+                // per-GT (max, lowest anchor index): IoU >= 0 so float bits order as integers.
+                // Only when some lane reaches the GT's current best does the warp reduce.
+                if (__any_sync(full, mybits >= cur[q])) {
+                    const unsigned m = __reduce_max_sync(full, mybits);
+                    unsigned cand = 0xffffffffu;
+#pragma unroll
+                    for (int j = kEncApt - 1; j >= 0; --j)
+                        if (bits[q][j] == m) cand = (unsigned)(j * 32 + lane);
+                    const unsigned first = __reduce_min_sync(full, cand);
+                    if (lane == 0) {
+                        u64 key = ((u64)m << 32) | (u64)(0xffffffffu - (set_c0 + first));
+                        atomicMax(&s_best[gq[q]], key);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int SETS, int SPLIT>
+__global__ void __launch_bounds__(kEncThreads, 10)
 match_encode_kernel(const __grid_constant__ EncodeParams p) {
+    static_assert(SETS * SPLIT == kEncWarps, "4 warps per CTA");
+    constexpr int kTile = SETS * kEncSet;
     extern __shared__ __align__(128) unsigned char smem[];
     float4* s_box = reinterpret_cast<float4*>(smem);              // [gcap] GT corners
     u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [gcap] per-GT (iou bits, ~compact anchor) of this tile
     float* s_area = reinterpret_cast<float*>(s_best + p.gcap);    // [gcap]
-    __shared__ float s_mv[kEncThreads * APT];                     // per-anchor max overlap of this tile
-    __shared__ int s_mg[kEncThreads * APT];                       // per-anchor first argmax (-1: none)
+    __shared__ float s_mv[SPLIT][kTile];                          // per-anchor max overlap, per GT part
+    __shared__ int s_mg[SPLIT][kTile];                            // per-anchor first argmax (-1: none)
     __shared__ int s_last;
 
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * (kEncThreads * APT);
-    const int warp_c0 = c0 + warp * (32 * APT);
-    // flat anchor range whose outputs this tile writes: from its first inside anchor up to the next tile's
-    const int n_lo = (blockIdx.x == 0) ? 0 : p.inside_idx[c0];
-    const int n_hi = (c0 + kEncThreads * APT >= p.Nin) ? p.N : p.inside_idx[c0 + kEncThreads * APT];
+    const int set = warp / SPLIT, part = warp % SPLIT;
+    const int b = blockIdx.x;
+    const float4* gtb = p.gt_boxes + (size_t)b * p.Gmax;
+    int G = p.gt_counts[b];
+    G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
 
-    // ---- this thread's anchors: corners + area in registers for the whole image loop
-    float4 a[APT];
-    float area[APT];
-    float wy0 = CUDART_INF_F, wx0 = CUDART_INF_F, wy1 = -CUDART_INF_F, wx1 = -CUDART_INF_F;
-#pragma unroll
-    for (int j = 0; j < APT; ++j) {
-        int c = warp_c0 + j * 32 + lane;
-        const bool in = c < p.Nin;
-        a[j] = in ? p.ccor[c] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-        area[j] = in ? (a[j].w - a[j].y) * (a[j].z - a[j].x) : 0.f;
-        wy0 = fminf(wy0, a[j].x);
-        wx0 = fminf(wx0, a[j].y);
-        wy1 = fmaxf(wy1, a[j].z);
-        wx1 = fmaxf(wx1, a[j].w);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        wy0 = fminf(wy0, __shfl_xor_sync(full, wy0, o));
-        wx0 = fminf(wx0, __shfl_xor_sync(full, wx0, o));
-        wy1 = fmaxf(wy1, __shfl_xor_sync(full, wy1, o));
-        wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
-    }
+    for (int tile = blockIdx.y; tile < p.tiles; tile += gridDim.y) {
+        const int c0 = tile * kTile;
+        const int set_c0 = c0 + set * kEncSet;
+        // flat anchor range whose outputs this tile writes: from its first inside anchor up to the next tile's
+        const int n_lo = (tile == 0) ? 0 : p.inside_idx[c0];
+        const int n_hi = (c0 + kTile >= p.Nin) ? p.N : p.inside_idx[c0 + kTile];
 
-    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {
-        const float4* gtb = p.gt_boxes + (size_t)b * p.Gmax;
-        int G = p.gt_counts[b];
-        G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
-        __syncthreads();                               // previous image is done with shared memory
+        __syncthreads();                               // previous tile is done with shared memory
+        bool nice = true;
         for (int g = tid; g < G; g += kEncThreads) {
             float4 v = gtb[g];
             s_box[g] = v;
             s_area[g] = (v.w - v.y) * (v.z - v.x);
-            s_best[g] = 0ull;
+            // start from the image-wide best published so far (any stale value is a valid lower
+            // bound): only overlaps that can still win reach the reduction path
+            s_best[g] = __ldcg(p.ws_keys + (size_t)b * p.Gmax + g);
+            nice = nice && nice_coord(v.x) && nice_coord(v.y) && nice_coord(v.z) && nice_coord(v.w);
         }
-        __syncthreads();
 
-        // ---- IoU sweep.  best/bestg: per-anchor running max and FIRST argmax over GT (strict
-        // '>' over ascending g == tf.argmax first occurrence).
-        float best[APT];
-        int bestg[APT];
+        // ---- this lane's anchors: corners + area in registers
+        float4 a[kEncApt];
+        float area[kEncApt];
+        float wy0 = CUDART_INF_F, wx0 = CUDART_INF_F, wy1 = -CUDART_INF_F, wx1 = -CUDART_INF_F;
 #pragma unroll
-        for (int j = 0; j < APT; ++j) { best[j] = 0.f; bestg[j] = -1; }
-
-        for (int g0 = 0; g0 < G; g0 += 32) {
-            bool touch = false;
-            if (g0 + lane < G) {
-                float4 t = s_box[g0 + lane];
-                touch = (fminf(t.z, wy1) > fmaxf(t.x, wy0)) && (fminf(t.w, wx1) > fmaxf(t.y, wx0));
-            }
-            unsigned todo = __ballot_sync(full, touch);
-            while (todo) {
-                // two GT boxes per iteration (the second repeats the first when only one is left:
-                // max / first-argmax / atomicMax are idempotent) for instruction-level parallelism
-                int gq[2];
-                gq[0] = g0 + __ffs(todo) - 1;
-                todo &= todo - 1;
-                gq[1] = todo ? g0 + __ffs(todo) - 1 : gq[0];
-                todo &= todo - 1;
-                float4 t[2];
-                float ga[2];
-                unsigned cur[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    t[q] = s_box[gq[q]];
-                    ga[q] = s_area[gq[q]];
-                    cur[q] = (unsigned)(s_best[gq[q]] >> 32);       // stale values are only lower: a safe filter
-                }
-                unsigned bits[2][APT];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                    for (int j = 0; j < APT; ++j) {
-                        float iou = iou_ref(t[q], ga[q], a[j], area[j]);
-                        bits[q][j] = __float_as_uint(iou);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    unsigned mybits = 0u;
-#pragma unroll
-                    for (int j = 0; j < APT; ++j) {
-                        float iou = __uint_as_float(bits[q][j]);
-                        if (iou > best[j]) { best[j] = iou; bestg[j] = gq[q]; }
-                        mybits = max(mybits, bits[q][j]);
-                    }
-                    // per-GT (max, lowest anchor index): IoU >= 0 so float bits order as integers.
-                    // Only when some lane reaches the GT's current best does the warp reduce.
-                    if (__any_sync(full, mybits != 0u && mybits >= cur[q])) {
-                        const unsigned m = __reduce_max_sync(full, mybits);
-                        unsigned cand = 0xffffffffu;
-#pragma unroll
-                        for (int j = APT - 1; j >= 0; --j)
-                            if (bits[q][j] == m) cand = (unsigned)(j * 32 + lane);
-                        const unsigned first = __reduce_min_sync(full, cand);
-                        if (lane == 0) {
-                            u64 key = ((u64)m << 32) | (u64)(0xffffffffu - ((unsigned)warp_c0 + first));
-                            atomicMax(&s_best[gq[q]], key);
-                        }
-                    }
-                }
-            }
+        for (int j = 0; j < kEncApt; ++j) {
+            int c = set_c0 + j * 32 + lane;
+            const bool in = c < p.Nin;
+            a[j] = in ? p.ccor[c] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+            area[j] = in ? (a[j].w - a[j].y) * (a[j].z - a[j].x) : 0.f;
+            wy0 = fminf(wy0, a[j].x);
+            wx0 = fminf(wx0, a[j].y);
+            wy1 = fmaxf(wy1, a[j].z);
+            wx1 = fmaxf(wx1, a[j].w);
         }
 #pragma unroll
-        for (int j = 0; j < APT; ++j) {
-            s_mv[warp * (32 * APT) + j * 32 + lane] = best[j];
-            s_mg[warp * (32 * APT) + j * 32 + lane] = bestg[j];
+        for (int o = 16; o > 0; o >>= 1) {
+            wy0 = fminf(wy0, __shfl_xor_sync(full, wy0, o));
+            wx0 = fminf(wx0, __shfl_xor_sync(full, wx0, o));
+            wy1 = fmaxf(wy1, __shfl_xor_sync(full, wy1, o));
+            wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
+        }
+        nice = __syncthreads_and(nice && p.anchors_nice) != 0;
+
+        float best[kEncApt];
+        int bestg[kEncApt];
+#pragma unroll
+        for (int j = 0; j < kEncApt; ++j) { best[j] = 0.f; bestg[j] = -1; }
+        const int per = (G + SPLIT - 1) / SPLIT;
+        const int g_lo = min(G, part * per), g_hi = min(G, g_lo + per);
+        if (nice)
+            sweep<true>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
+        else
+            sweep<false>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
+#pragma unroll
+        for (int j = 0; j < kEncApt; ++j) {
+            s_mv[part][set * kEncSet + j * 32 + lane] = best[j];
+            s_mg[part][set * kEncSet + j * 32 + lane] = bestg[j];
         }
         __syncthreads();
 
         for (int g = tid; g < G; g += kEncThreads) {
             u64 v = s_best[g];
-            if (v != 0ull) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
+            // only keys this tile produced are above the value it started from
+            if (v != 0ull && v > __ldcg(p.ws_keys + (size_t)b * p.Gmax + g)) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
         }
 
         // ---- label + encode + store the tile's flat anchor range (forced anchors are rewritten
@@ -261,8 +300,13 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             float mv = 0.f;
             int a2g = 0;
             if (c >= 0) {
-                mv = s_mv[c - c0];
-                int g = s_mg[c - c0];
+                // parts hold ascending GT ranges: strict '>' keeps the lowest GT index on ties
+                int g = -1;
+#pragma unroll
+                for (int s = 0; s < SPLIT; ++s) {
+                    float v = s_mv[s][c - c0];
+                    if (v > mv) { mv = v; g = s_mg[s][c - c0]; }
+                }
                 a2g = g < 0 ? 0 : g;
             }
             bool less = mv < p.low;
@@ -288,12 +332,13 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
             if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
         }
 
-        // ---- publish; the last tile of the image applies the per-GT forcing
-        __threadfence();
+        // ---- publish; the last tile of the image applies the per-GT forcing.  Barrier first, then
+        // one thread fences and bumps the counter (release pattern of a grid-wide barrier).
         __syncthreads();
         if (tid == 0) {
+            __threadfence();
             unsigned prev = atomicAdd(p.ws_count + b, 1u);
-            s_last = (prev == gridDim.x - 1) ? 1 : 0;
+            s_last = (prev == (unsigned)p.tiles - 1u) ? 1 : 0;
         }
         __syncthreads();
         if (s_last) {
@@ -367,18 +412,28 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     p.ws_claimed = (unsigned*)((u64*)ws + (size_t)B * Gmax);
     p.ws_count = p.ws_claimed + (size_t)B * Gmax;
 
-    int tiles = (p.Nin + kEncTile - 1) / kEncTile;
-    if (tiles < 1) tiles = 1;
-    // image groups: every CTA keeps its anchors in registers and loops over images; aim at a few
-    // waves of resident CTAs so the hardware scheduler balances the uneven (G-dependent) work
-    long long want = (long long)h->num_sms * 8 * 4;
-    int ipc = (int)(((long long)B * tiles) / want);
-    if (ipc < 1) ipc = 1;
-    int Q = (B + ipc - 1) / ipc;
-    if (Q > 65535) Q = 65535;
+    p.anchors_nice = h->anchors_nice;
+    // Small batches cannot fill 148 SMs x 32 warps with whole-GT-list items: split the GT list of
+    // every 64-anchor set over the CTA's four warps instead (4x more, 4x shorter items).
+    const int sets_total = (p.Nin + kEncSet - 1) / kEncSet;
+    const long long items = (long long)B * sets_total, slots = (long long)h->num_sms * 32;
+    int split = items < slots * 2 ? 4 : (items < slots * 6 ? 2 : 1);
+    if (const char* e = getenv("RONK_ENC_SPLIT")) {          // tuning knob (1, 2 or 4)
+        int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) split = v;
+    }
+    const int tile_anchors = (kEncWarps / split) * kEncSet;
+    p.tiles = (p.Nin + tile_anchors - 1) / tile_anchors;
+    if (p.tiles < 1) p.tiles = 1;
     size_t smem = (size_t)p.gcap * (16 + 8 + 4);
     cudaStream_t st = (cudaStream_t)stream;
-    match_encode_kernel<kEncApt><<<dim3(tiles, Q), kEncThreads, smem, st>>>(p);
+    dim3 grid((unsigned)B, (unsigned)(p.tiles < 65535 ? p.tiles : 65535));
+    if (split == 4)
+        match_encode_kernel<1, 4><<<grid, kEncThreads, smem, st>>>(p);
+    else if (split == 2)
+        match_encode_kernel<2, 2><<<grid, kEncThreads, smem, st>>>(p);
+    else
+        match_encode_kernel<4, 1><<<grid, kEncThreads, smem, st>>>(p);
     RONK_LAUNCHED();
     return RONK_OK;
 }

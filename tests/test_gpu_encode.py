@@ -157,3 +157,47 @@ def test_property_full_size_batch256(ron):
     for b in range(0, 256, 17):
         owned = torch.unique(m[b][m[b] >= 0])
         assert owned.numel() == int(cnt[b]), 'image %d: every GT must be matched by at least one anchor' % b
+
+
+def test_encode_batch256_vs_oracle_sampled(ron):
+    """The large-batch kernel variant (4 anchor sets per CTA, no GT split) against the oracle on a
+    sample of the 256 images, bit-exact."""
+    net, anchors = ron
+    boxes, labels, counts = synth.make_gt_batch(2, 256, 1, 50)
+    r = net.bboxes_encode_batch(labels, boxes, counts, anchors, 0.56, 0.3, want_matched=True)
+    _, (enc, cor, inside) = _oracle_tables(O.RON320)
+    for b in list(range(0, 256, 13)) + [255]:
+        o = O.encode_image(labels[b, :counts[b]], boxes[b, :counts[b]], enc, cor, inside, 0.56, 0.3)
+        eq(r['matched'][b], o['matched'].astype(np.int32), 'matched[%d]' % b)
+        eq(r['labels'][b], o['labels'], 'labels[%d]' % b)
+        eq(r['scores'][b], o['scores'], 'scores[%d]' % b)
+        eq(r['loc'][b], o['loc'], 'loc[%d]' % b)
+
+
+@pytest.mark.parametrize('batch', [3, 160])
+def test_encode_extreme_coordinates(ron, batch):
+    """GT boxes with tiny coordinates / tiny sides / zero area (outside the range where the inline
+    division sequence is proven exact: the kernel must switch to IEEE division) and duplicated GT
+    boxes (exact ties between GT rows), both kernel variants."""
+    net, anchors = ron
+    boxes, labels, counts = synth.make_gt_batch(7, batch, 3, 12)
+    boxes = boxes.copy()
+    for b in range(batch):
+        k = b % 4
+        if k == 0:
+            boxes[b, 0] = [1e-7, 3e-6, 0.4, 0.5]                 # tiny non-zero corner
+        elif k == 1:
+            boxes[b, 1] = [0.25, 0.25, 0.25 + 1e-6, 0.75]        # sliver
+        elif k == 2:
+            boxes[b, 2] = boxes[b, 0]                            # duplicate GT: lower index must win
+        else:
+            boxes[b, 1] = [0.5, 0.5, 0.5, 0.5]                   # zero area
+    r = net.bboxes_encode_batch(labels, boxes, counts, anchors, 0.5, 0.3, want_matched=True)
+    _, (enc, cor, inside) = _oracle_tables(O.RON320)
+    for b in range(0, batch, max(1, batch // 12)):
+        with np.errstate(all='ignore'):
+            o = O.encode_image(labels[b, :counts[b]], boxes[b, :counts[b]], enc, cor, inside, 0.5, 0.3)
+        eq(r['matched'][b], o['matched'].astype(np.int32), 'matched[%d]' % b)
+        eq(r['labels'][b], o['labels'], 'labels[%d]' % b)
+        eq(r['scores'][b], o['scores'], 'scores[%d]' % b)
+        eq(r['loc'][b], o['loc'], 'loc[%d]' % b)
