@@ -32,7 +32,9 @@ struct PostParams {
     float4 clip;
     float ps0, ps1, ps2, ps3;
     int* counts;                     // [B*(C-1)]
+    float* thr;                      // [B*(C-1)] score threshold of every (image, class): sel_thr, or a sampled pivot
     u64* keys;                       // [B*(C-1), cap]
+    float4* boxes;                   // [B, N] final (decoded, clipped) box of every surviving anchor
     int cap;
     long long num_tiles;
     float* out_scores;
@@ -75,11 +77,10 @@ struct TileInfo {
     long long start_w, a0, a1, end_w;   // word offsets inside the layer's class array
 };
 
-__device__ __forceinline__ TileInfo tile_info(const PostParams& p, long long tile) {
+// tile r of image b (r in [0, tiles per image))
+__device__ __forceinline__ TileInfo tile_info(const PostParams& p, int b, int r) {
     TileInfo t;
-    const int tpi = p.tile_off[p.tab.L];
-    t.b = (int)(tile / tpi);
-    int r = (int)(tile % tpi);
+    t.b = b;
     int l = 0;
     while (l + 1 < p.tab.L && r >= p.tile_off[l + 1]) ++l;
     t.layer = l;
@@ -97,17 +98,126 @@ __device__ __forceinline__ TileInfo tile_info(const PostParams& p, long long til
     return t;
 }
 
-__global__ void __launch_bounds__(kTileRows)
+constexpr int kScatWarps = kTileRows / 32;
+
+// Class-major scan of one tile by one warp (slow, fully general form: used for the few tiles
+// whose last <= 3 score words are not covered by the 16-byte granular bulk copy and must be read
+// from global memory).  One atomic per (class, chunk of 32 surviving rows).
+__device__ __noinline__ void class_scan_tail(const PostParams& p, const TileInfo& t, const float* s_cls,
+                                             const int* s_rows, const unsigned* s_vmask, int n_gated, int nchunks) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = p.C;
+    const int wlim = (int)(t.a1 - t.start_w);   // words of this tile that sit in smem
+    const float* gcls = p.cls[t.layer] + t.start_w;
+    const unsigned nkey0 = 0xffffffffu - (unsigned)(p.tab.offs[t.layer] + t.t0);
+    for (int c = 1 + warp; c < C; c += kScatWarps) {
+        int* cnt = p.counts + (size_t)t.b * (C - 1) + (c - 1);
+        u64* dst = p.keys + ((size_t)t.b * (C - 1) + (c - 1)) * p.cap;
+        for (int k = 0; k < nchunks; ++k) {
+            const int i = k * 32 + lane;
+            bool pass = false;
+            float v = 0.f;
+            int r = 0;
+            if (i < n_gated && ((s_vmask[k] >> lane) & 1u)) {
+                r = s_rows[i];
+                const int e = r * C + c;
+                v = (e < wlim) ? s_cls[e] : gcls[e];
+                pass = v > p.thr[(size_t)t.b * (C - 1) + (c - 1)];
+            }
+            const unsigned m = __ballot_sync(full, pass);
+            if (m == 0u) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cnt, __popc(m));
+            base = __shfl_sync(full, base, 0);
+            if (pass) dst[base + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(v) << 32) | (u64)(nkey0 - (unsigned)r);
+        }
+    }
+}
+
+// Fast form, NCH = number of 32-row chunks of surviving rows (compile-time, so the per-lane row
+// state lives in registers).  Per group of up to 32 classes of this warp: pass 1 counts the passing
+// rows of every class (ballots only), then lane j reserves class j's slots -- all atomics of the
+// group are in flight together, one round trip -- and pass 2 writes the u64 keys.
+template <int NCH>
+__device__ __forceinline__ void class_scan(const PostParams& p, const TileInfo& t, const float* s_cls,
+                                           const int* s_rows, const unsigned* s_vmask, int n_gated) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = p.C, CM = p.C - 1;
+    const unsigned nkey0 = 0xffffffffu - (unsigned)(p.tab.offs[t.layer] + t.t0);
+    const unsigned lt = (1u << lane) - 1u;
+    const float* row[NCH];      // this lane's surviving row of chunk k (scores), or the tile start when none
+    unsigned nk[NCH];           // low word of the key
+    unsigned ok = 0u;           // bit k: this lane has a valid surviving row in chunk k
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int i = k * 32 + lane;
+        int r = 0;
+        if (i < n_gated && ((s_vmask[k] >> lane) & 1u)) {
+            r = s_rows[i];
+            ok |= 1u << k;
+        }
+        row[k] = s_cls + r * C;
+        nk[k] = nkey0 - (unsigned)r;
+    }
+    const size_t seg0 = (size_t)t.b * CM;
+    for (int c0 = 1 + warp; c0 < C; c0 += 32 * kScatWarps) {
+        // ---- pass 1: totals (lane j keeps the total of class c0 + 8 j)
+        int mytotal = 0;
+        int j = 0;
+        for (int c = c0; c < C && j < 32; c += kScatWarps, ++j) {
+            const float thr = p.thr[seg0 + (c - 1)];
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const bool pass = ((ok >> k) & 1u) && row[k][c] > thr;
+                total += __popc(__ballot_sync(full, pass));
+            }
+            if (lane == j) mytotal = total;
+        }
+        const int myc = c0 + lane * kScatWarps;
+        int mybase = 0;
+        if (mytotal > 0) mybase = atomicAdd(p.counts + seg0 + (myc - 1), mytotal);
+        // ---- pass 2: keys
+        j = 0;
+        for (int c = c0; c < C && j < 32; c += kScatWarps, ++j) {
+            int pos = __shfl_sync(full, mybase, j);
+            if (__shfl_sync(full, mytotal, j) == 0) continue;
+            const float thr = p.thr[seg0 + (c - 1)];
+            u64* dst = p.keys + (seg0 + (c - 1)) * p.cap;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const float v = row[k][c];
+                const bool pass = ((ok >> k) & 1u) && v > thr;
+                const unsigned m = __ballot_sync(full, pass);
+                if (pass) dst[pos + __popc(m & lt)] = ((u64)__float_as_uint(v) << 32) | (u64)nk[k];
+                pos += __popc(m);
+            }
+        }
+    }
+}
+
+// One tile = 256 consecutive anchors of one layer of one image, all C class scores.
+//  A. every thread gates its own row by objectness; the surviving rows are compacted
+//     (ballot + warp prefix) into s_rows, so that the two expensive steps below run on full warps;
+//  B. one thread per SURVIVING row decodes + clips + size-tests the box (two float64 exp) from the
+//     localisation rows that arrived with the same TMA transaction as the scores, and stores the
+//     box to the per-image box table (the top-k kernel gathers its winners from it);
+//  C. class-major scan (class_scan above): warp w owns classes 1+w, 1+w+8, ...
+__global__ void __launch_bounds__(kTileRows, 4)
 scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int C = p.C, CM = p.C - 1;
+    const int C = p.C;
     const int stage_floats = (kTileRows * C + 4 + 3) & ~3;
-    float* const s_stage0 = reinterpret_cast<float*>(smem);
-    int* s_wcnt = reinterpret_cast<int*>(reinterpret_cast<float*>(smem) + 2 * stage_floats);   // [8][CM]
-    int* s_wbase = s_wcnt + 8 * CM;                                                           // [8][CM]
+    const int stage_bytes = stage_floats * 4 + kTileRows * 16;     // scores | loc rows
     __shared__ __align__(8) u64 s_bar[2];
+    __shared__ int s_rows[kTileRows];
+    __shared__ int s_wcnt[kScatWarps];
+    __shared__ unsigned s_vmask[kScatWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -115,115 +225,107 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     }
     __syncthreads();
 
-    long long tile = blockIdx.x;
-    if (tile >= p.num_tiles) return;
-    if (tid == 0) {
-        TileInfo t = tile_info(p, tile);
-        unsigned bytes = (unsigned)((t.a1 - t.a0) * 4);
-        if (bytes) {
-            mbar_arrive_expect_tx(&s_bar[0], bytes);
-            tma_load_1d(s_stage0, p.cls[t.layer] + t.a0, bytes, &s_bar[0]);
-        }
-    }
+    auto issue = [&](const TileInfo& t, int st) {
+        // thread 0 only: one mbarrier transaction = score tile + localisation rows
+        unsigned char* base = smem + (size_t)st * stage_bytes;
+        unsigned cls_bytes = (unsigned)((t.a1 - t.a0) * 4);
+        unsigned row_bytes = (unsigned)t.rows * 16u;
+        mbar_arrive_expect_tx(&s_bar[st], cls_bytes + row_bytes);
+        if (cls_bytes) tma_load_1d(base, p.cls[t.layer] + t.a0, cls_bytes, &s_bar[st]);
+        const size_t row = (size_t)t.b * t.n_l + t.t0;
+        tma_load_1d(base + stage_floats * 4, reinterpret_cast<const float4*>(p.loc[t.layer]) + row, row_bytes, &s_bar[st]);
+    };
+    auto load_gate = [&](const TileInfo& t) -> bool {
+        bool gate = tid < t.rows;
+        if (gate && p.has_obj) gate = p.obj[t.layer][(size_t)t.b * t.n_l + t.t0 + tid] > p.obj_thr;
+        return gate;
+    };
+
+    // tiles are visited grid-stride; (b, r) = (image, tile inside the image) advances without divisions
+    const int tpi = p.tile_off[p.tab.L];
+    const int step_b = (int)(gridDim.x / (unsigned)tpi), step_r = (int)(gridDim.x % (unsigned)tpi);
+    int b = (int)(blockIdx.x / (unsigned)tpi), r = (int)(blockIdx.x % (unsigned)tpi);
+    if (b >= p.B) return;
+    TileInfo t = tile_info(p, b, r);
+    if (tid == 0) issue(t, 0);
+    bool gate = load_gate(t);
     unsigned phase = 0u;   // bit st = parity the next wait on stage st must see
-    for (int it = 0; tile < p.num_tiles; ++it, tile += gridDim.x) {
+    for (int it = 0; b < p.B; ++it) {
         const int st = it & 1;
         // prefetch the next tile into the other stage (freed by the barrier that ended iteration it-1)
-        const long long next = tile + gridDim.x;
-        if (tid == 0 && next < p.num_tiles) {
-            TileInfo tn = tile_info(p, next);
-            unsigned bytes = (unsigned)((tn.a1 - tn.a0) * 4);
-            if (bytes) {
-                mbar_arrive_expect_tx(&s_bar[st ^ 1], bytes);
-                tma_load_1d(s_stage0 + (st ^ 1) * stage_floats, p.cls[tn.layer] + tn.a0, bytes, &s_bar[st ^ 1]);
-            }
-        }
-        const TileInfo t = tile_info(p, tile);
-        const int nl = t.t0 + tid;
-        const bool rowok = tid < t.rows;
-        const int n = p.tab.offs[t.layer] + nl;
-        const size_t row = (size_t)t.b * t.n_l + nl;
-
-        // independent global loads first, so they overlap the wait for the bulk copy
-        bool gate = rowok;
-        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = l4;
-        if (rowok) {
-            if (p.has_obj) gate = p.obj[t.layer][row] > p.obj_thr;
-            if (gate) {
-                l4 = reinterpret_cast<const float4*>(p.loc[t.layer])[row];
-                a4 = p.dec[n];
-            }
-        }
-        if (t.a1 > t.a0) {
-            mbar_wait(&s_bar[st], (phase >> st) & 1u);
-            phase ^= 1u << st;
+        int nb = b + step_b, nr = r + step_r;
+        if (nr >= tpi) { nr -= tpi; ++nb; }
+        TileInfo tn = t;
+        bool gate_next = false;
+        if (nb < p.B) {
+            tn = tile_info(p, nb, nr);
+            if (tid == 0) issue(tn, st ^ 1);
+            gate_next = load_gate(tn);          // objectness of the next tile: the load overlaps this tile's work
         }
 
-        const float* srow = s_stage0 + st * stage_floats + (t.start_w - t.a0) + (long long)tid * C;
-        const float* grow = p.cls[t.layer] + t.start_w + (long long)tid * C;
-        const bool tail = t.end_w > t.a1;   // last <=3 words of the layer array are not covered by the bulk copy
-        const long long wlim = t.a1 - t.start_w - (long long)tid * C;   // words of this row that sit in smem
+        // ---- A. objectness gate + compaction of the surviving rows
+        const unsigned gmask = __ballot_sync(full, gate);
+        if (lane == 0) s_wcnt[warp] = __popc(gmask);
+        __syncthreads();
+        int gbase = 0, n_gated = 0;
+#pragma unroll
+        for (int w = 0; w < kScatWarps; ++w) {
+            int c = s_wcnt[w];
+            gbase += (w < warp) ? c : 0;
+            n_gated += c;
+        }
+        if (gate) s_rows[gbase + __popc(gmask & ((1u << lane) - 1u))] = tid;
+        mbar_wait(&s_bar[st], (phase >> st) & 1u);
+        phase ^= 1u << st;
+        __syncthreads();
 
-        bool any = false;
-        if (gate) {
-            for (int c = 1; c < C; ++c) {
-                float v = (!tail || c < wlim) ? srow[c] : grow[c];
-                any |= v > p.sel_thr;
+        const unsigned char* base = smem + (size_t)st * stage_bytes;
+        const float* s_cls = reinterpret_cast<const float*>(base) + (int)(t.start_w - t.a0);
+        const float4* s_loc = reinterpret_cast<const float4*>(base + stage_floats * 4);
+        const int nchunks = (n_gated + 31) >> 5;
+
+        // ---- B. boxes of the surviving rows (compacted: thread i <-> row s_rows[i])
+        if (warp < nchunks) {
+            bool valid = false;
+            if (tid < n_gated) {
+                const int rr = s_rows[tid];
+                const int n = p.tab.offs[t.layer] + t.t0 + rr;
+                float4 box = p.decoded ? s_loc[rr] : decode_box(s_loc[rr], p.dec[n], p.ps0, p.ps1, p.ps2, p.ps3);
+                if (p.has_clip) box = clip_box(box, p.clip);
+                valid = true;
+                if (p.min_size >= 0.f) {
+                    float h = box.z - box.x;
+                    float w = box.w - box.y;
+                    valid = (w > p.min_size) && (h > p.min_size);
+                }
+                if (valid) p.boxes[(size_t)t.b * p.tab.N + n] = box;
             }
-        }
-        bool valid = false;
-        u64 nkey = (u64)(0xffffffffu - (unsigned)n);
-        if (any) {
-            float4 box = p.decoded ? l4 : decode_box(l4, a4, p.ps0, p.ps1, p.ps2, p.ps3);
-            if (p.has_clip) box = clip_box(box, p.clip);
-            valid = true;
-            if (p.min_size >= 0.f) {
-                float h = box.z - box.x;
-                float w = box.w - box.y;
-                valid = (w > p.min_size) && (h > p.min_size);
-            }
-        }
-        // phase 1: per-warp, per-class candidate counts
-        for (int c = 1; c < C; ++c) {
-            bool pass = false;
-            if (valid) {
-                float v = (!tail || c < wlim) ? srow[c] : grow[c];
-                pass = v > p.sel_thr;
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (lane == 0) s_wcnt[warp * CM + (c - 1)] = __popc(bal);
+            const unsigned vm = __ballot_sync(full, valid);
+            if (lane == 0) s_vmask[warp] = vm;
         }
         __syncthreads();
-        // one global atomic per class per CTA reserves the tile's slots in the (image, class) list
-        for (int c = tid; c < CM; c += kTileRows) {
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) tot += s_wcnt[w * CM + c];
-            int base = 0;
-            if (tot) base = atomicAdd(p.counts + (size_t)t.b * CM + c, tot);
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                s_wbase[w * CM + c] = base;
-                base += s_wcnt[w * CM + c];
+
+        // ---- C. class-major scan over the compacted rows
+        if (t.end_w > t.a1) {
+            class_scan_tail(p, t, s_cls, s_rows, s_vmask, n_gated, nchunks);
+        } else {
+            switch (nchunks) {
+                case 0: break;
+                case 1: class_scan<1>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                case 2: class_scan<2>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                case 3: class_scan<3>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                case 4: class_scan<4>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                case 5: class_scan<5>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                case 6: class_scan<6>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                case 7: class_scan<7>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
+                default: class_scan<8>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
             }
         }
-        __syncthreads();
-        // phase 2: write keys
-        for (int c = 1; c < C; ++c) {
-            bool pass = false;
-            float v = 0.f;
-            if (valid) {
-                v = (!tail || c < wlim) ? srow[c] : grow[c];
-                pass = v > p.sel_thr;
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (pass) {
-                int pos = s_wbase[warp * CM + (c - 1)] + __popc(bal & ((1u << lane) - 1u));
-                if (pos < p.cap)
-                    p.keys[((size_t)t.b * CM + (c - 1)) * p.cap + pos] = ((u64)__float_as_uint(v) << 32) | nkey;
-            }
-        }
-        __syncthreads();   // stage st and the count arrays are free again
+        __syncthreads();   // stage st, s_rows and s_vmask are free again
+        t = tn;
+        b = nb;
+        r = nr;
+        gate = gate_next;
     }
 }
 
@@ -235,37 +337,265 @@ struct ListSrc {
     __device__ __forceinline__ u64 get(int i) const { return i < staged ? s[i] : g[i]; }
 };
 
-__device__ __forceinline__ float4 redecode_box(const PostParams& p, int b, int n) {
-    int l = layer_of(p.tab, n);
-    int n_l = p.tab.offs[l + 1] - p.tab.offs[l];
-    size_t row = (size_t)b * n_l + (n - p.tab.offs[l]);
-    float4 l4 = reinterpret_cast<const float4*>(p.loc[l])[row];
-    float4 box = p.decoded ? l4 : decode_box(l4, p.dec[n], p.ps0, p.ps1, p.ps2, p.ps3);
-    if (p.has_clip) box = clip_box(box, p.clip);
-    return box;
+constexpr int kListCap = 4096;                               // survivors of the sampling pre-filter (shared memory)
+constexpr int kKeysPerThread = kListCap / kTopkThreads;      // 16
+constexpr int kSample = 2 * kTopkThreads;                    // 512 sampled keys
+constexpr int kDigitBits = 11;
+constexpr int kBins = 1 << kDigitBits;
+
+// need-th largest of the keys held in registers across the block (zero = empty slot; the keys are
+// distinct).  MSD radix select with 11-bit digits -- the first digit is sign + exponent + 2 mantissa
+// bits of the score, so two passes almost always isolate the key -- warp-aggregated shared-memory
+// histogram, block scan from the top bin.  Returns thr with #{key >= thr} == need (the low bits of
+// thr are zero when a whole bucket is taken).  Requires need <= number of non-zero keys.
+template <int KPT>
+__device__ u64 radix_kth(const u64 (&key)[KPT], int nper, int need, unsigned* s_hist, int* s_ctl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    __shared__ unsigned s_wtot[kTopkThreads / 32];
+    u64 prefix = 0ull, mask = 0ull;
+    for (int shift = 64 - kDigitBits;; shift = max(shift - kDigitBits, 0)) {
+        const int width = (shift == 0) ? (64 % kDigitBits ? 64 % kDigitBits : kDigitBits) : kDigitBits;
+        const unsigned dmask = (1u << width) - 1u;
+        for (int i = tid; i < kBins; i += kTopkThreads) s_hist[i] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            if (j < nper) {
+                const bool act = key[j] != 0ull && (key[j] & mask) == prefix;
+                const unsigned d = (unsigned)(key[j] >> shift) & dmask;
+                // warp-aggregated histogram: one atomic per distinct digit per warp
+                const unsigned amask = __ballot_sync(full, act);
+                if (act) {
+                    const unsigned peers = __match_any_sync(amask, d);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], (unsigned)__popc(peers));
+                }
+            }
+        }
+        __syncthreads();
+        // thread t owns bins [kBins-1-8t-7, kBins-1-8t] (descending); find the bin where the count of
+        // keys in larger bins is < need <= that count + hist[bin]
+        constexpr int BPT = kBins / kTopkThreads;
+        unsigned cnt[BPT];
+        unsigned sum = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            cnt[q] = s_hist[kBins - 1 - (tid * BPT + q)];
+            sum += cnt[q];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        unsigned above = incl - sum;
+#pragma unroll
+        for (int w = 0; w < kTopkThreads / 32; ++w) above += (w < warp) ? s_wtot[w] : 0u;
+        if (above < (unsigned)need && (unsigned)need <= above + sum) {
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) {
+                if (above < (unsigned)need && (unsigned)need <= above + cnt[q]) {
+                    s_ctl[0] = kBins - 1 - (tid * BPT + q);
+                    s_ctl[1] = need - (int)above;
+                    s_ctl[2] = (cnt[q] == (unsigned)need - above) ? 1 : 0;
+                    above = 0xffffffffu;   // stop
+                } else if (above != 0xffffffffu) {
+                    above += cnt[q];
+                }
+            }
+        }
+        __syncthreads();
+        const int d = s_ctl[0];
+        need = s_ctl[1];
+        const int whole = s_ctl[2];
+        prefix |= (u64)(unsigned)d << shift;
+        mask |= (u64)dmask << shift;
+        if (whole || shift == 0) break;
+    }
+    __syncthreads();
+    return prefix;
 }
 
-constexpr int kStageKeys = 4096;
+// append sel keys to list (warp-aggregated: one shared atomic per warp per call)
+__device__ __forceinline__ void warp_append(bool sel, u64 key, u64* list, int cap, int* counter) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(full, sel);
+    if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, __popc(m));
+        base = __shfl_sync(full, base, 0);
+        if (sel) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) list[pos] = key;
+        }
+    }
+}
 
+// bitonic sort of s_sort[0..P), descending, through shared memory (any power of two P)
+__device__ __forceinline__ void block_bitonic_desc(u64* s_sort, int P) {
+    const int tid = threadIdx.x;
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (P >> 1); i += kTopkThreads) {
+                int lo = 2 * i - (i & (stride - 1));
+                int hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                u64 x = s_sort[lo], y = s_sort[hi];
+                if ((x < y) == desc) { s_sort[lo] = y; s_sort[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// The same network for P = 256 * EPT with the elements in registers (thread t owns elements
+// EPT*t .. EPT*t+EPT-1): strides below EPT stay inside the thread, strides below 32*EPT are warp
+// shuffles, only the log2(256/32) coarsest strides of each merge go through shared memory.
+template <int EPT>
+__device__ __forceinline__ void block_bitonic_regs(u64* s_sort) {
+    constexpr int P = kTopkThreads * EPT;
+    const int tid = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    u64 v[EPT];
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) v[r] = s_sort[EPT * tid + r];
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32 * EPT) {
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) s_sort[EPT * tid + r] = v[r];
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int e = EPT * tid + r;
+                    const u64 o = s_sort[e ^ stride];
+                    const bool keep_max = (((e & stride) == 0) == ((e & size) == 0));
+                    v[r] = (keep_max == (o > v[r])) ? o : v[r];
+                }
+            } else if (stride >= EPT) {
+                const int lm = stride / EPT;
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    const int e = EPT * tid + r;
+                    const u64 o = __shfl_xor_sync(full, v[r], lm);
+                    const bool keep_max = (((e & stride) == 0) == ((e & size) == 0));
+                    v[r] = (keep_max == (o > v[r])) ? o : v[r];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < EPT; ++r) {
+                    if ((r & stride) == 0) {
+                        const int e = EPT * tid + r;
+                        const bool desc = ((e & size) == 0);
+                        const u64 x = v[r], y = v[r | stride];
+                        if ((x < y) == desc) { v[r] = y; v[r | stride] = x; }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) s_sort[EPT * tid + r] = v[r];
+    __syncthreads();
+}
+
+// One CTA per (image, class): exact top-K of the candidate list, sorted descending
+// (tf.nn.top_k order: lower anchor first among equal scores), boxes gathered from the box table.
+//   n <= K            every key is a winner;
+//   n <= 4096         keys in registers, radix select of the K-th key;
+//   longer lists      a strided sample of 512 keys gives a pivot that is below the K-th key with
+//                     overwhelming probability (rank = expected + 4 sigma + 8); one streaming pass keeps
+//                     the keys >= pivot in shared memory, and the select runs on those.  If the pivot
+//                     turns out too high (fewer than K survivors) or too low (more than 4096), the
+//                     generic 8-bit radix select over the whole list takes over -- always exact.
 __global__ void __launch_bounds__(kTopkThreads)
 select_topk_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    u64* s_sort = reinterpret_cast<u64*>(smem);                 // pow2(K)
-    u64* s_keys = s_sort + next_pow2(p.K);                      // kStageKeys
-    __shared__ unsigned s_hist[256];
+    const int P = next_pow2(p.K);
+    u64* s_sort = reinterpret_cast<u64*>(smem);                          // P
+    u64* s_list = s_sort + P;                                            // kListCap
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_list + kListCap);   // kBins
     __shared__ int s_ctl[4];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
     const int seg = blockIdx.x;
     const int CM = p.C - 1;
     const int b = seg / CM;
     int n = p.counts[seg];
     n = n > p.cap ? p.cap : n;
     const u64* g = p.keys + (size_t)seg * p.cap;
-    const int staged = n < kStageKeys ? n : kStageKeys;
-    for (int i = threadIdx.x; i < staged; i += kTopkThreads) s_keys[i] = g[i];
+    for (int i = tid; i < P; i += kTopkThreads) s_sort[i] = 0ull;
+    if (tid == 0) { s_cnt = 0; s_ctl[3] = 0; }
     __syncthreads();
-    ListSrc src{g, s_keys, staged};
-    block_topk_sorted(src, n, p.K, s_hist, s_ctl, s_sort);
-    for (int r = threadIdx.x; r < p.K; r += kTopkThreads) {
+
+    bool sorted = false;
+    if (n <= p.K) {
+        for (int i = tid; i < n; i += kTopkThreads) s_sort[i] = g[i];
+        __syncthreads();
+    } else {
+        const u64* src = g;
+        int m = n;
+        bool generic = false;
+        if (n > kListCap || (n > 4 * p.K && n > 1024)) {
+            // ---- sampling pre-filter
+            const float mu = (float)p.K * (float)kSample / (float)n;
+            int R = (int)(mu + 4.f * sqrtf(mu) + 8.f);
+            u64 pivot = 1ull;
+            if (R < kSample) {
+                u64 ks[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) ks[j] = g[(int)(((long long)(j * kTopkThreads + tid) * n) / kSample)];
+                pivot = radix_kth<2>(ks, 2, R, s_hist, s_ctl);
+            }
+            for (int i0 = 0; i0 < n; i0 += kTopkThreads) {
+                const int i = i0 + tid;
+                u64 k = (i < n) ? g[i] : 0ull;
+                warp_append(k >= pivot && k != 0ull, k, s_list, kListCap, &s_cnt);
+            }
+            __syncthreads();
+            m = s_cnt;
+            src = s_list;
+            generic = (m < p.K) || (m > kListCap);
+        }
+        if (generic) {
+            // pivot too high / too low, or K itself beyond the register path: 8-bit radix select over the whole list
+            ListSrc all{g, nullptr, 0};
+            block_topk_sorted(all, n, p.K, s_hist, s_ctl, s_sort);
+            sorted = true;
+        } else if (m <= p.K) {
+            for (int i = tid; i < m; i += kTopkThreads) s_sort[i] = src[i];
+            __syncthreads();
+        } else {
+            u64 key[kKeysPerThread];
+            const int nper = (m + kTopkThreads - 1) / kTopkThreads;
+#pragma unroll
+            for (int j = 0; j < kKeysPerThread; ++j) {
+                key[j] = 0ull;
+                if (j < nper) {
+                    const int i = j * kTopkThreads + tid;
+                    if (i < m) key[j] = src[i];
+                }
+            }
+            const u64 thr = radix_kth<kKeysPerThread>(key, nper, p.K, s_hist, s_ctl);
+#pragma unroll
+            for (int j = 0; j < kKeysPerThread; ++j)
+                if (j < nper) warp_append(key[j] != 0ull && key[j] >= thr, key[j], s_sort, P, &s_ctl[3]);
+            __syncthreads();
+        }
+    }
+    if (!sorted) {
+        if (P == kTopkThreads) block_bitonic_regs<1>(s_sort);
+        else if (P == 2 * kTopkThreads) block_bitonic_regs<2>(s_sort);
+        else if (P == 4 * kTopkThreads) block_bitonic_regs<4>(s_sort);
+        else block_bitonic_desc(s_sort, P);
+    }
+    for (int r = tid; r < p.K; r += kTopkThreads) {
         u64 k = s_sort[r];
         float sc = 0.f;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -273,7 +603,7 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
         if (k != 0ull) {
             sc = __uint_as_float((unsigned)(k >> 32));
             idx = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
-            box = redecode_box(p, b, idx);
+            box = p.boxes[(size_t)b * p.tab.N + idx];
         }
         size_t o = (size_t)seg * p.K + r;
         p.out_scores[o] = sc;
@@ -282,9 +612,12 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
     }
 }
 
-__global__ void zero_i32_kernel(int* p, size_t n) {
+__global__ void init_segments_kernel(int* counts, float* thr, float sel_thr, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0;
+    if (i < n) {
+        counts[i] = 0;
+        thr[i] = sel_thr;
+    }
 }
 
 // ------------------------------------------------------------------ stand-alone decode / clip
@@ -354,7 +687,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 extern "C" size_t ronk_select_workspace_bytes(const ronk_anchors_t* h, int B, int C, int K) {
     if (!h || B < 1 || C < 2 || K < 1) return 0;
     size_t segs = (size_t)B * (C - 1);
-    return align_up(segs * sizeof(int), 256) + segs * (size_t)h->tab.N * sizeof(u64);
+    return 2 * align_up(segs * sizeof(int), 256) + segs * (size_t)h->tab.N * sizeof(u64) + (size_t)B * h->tab.N * 16;
 }
 
 extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* const* loc_layers,
@@ -402,23 +735,26 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     p.ps0 = ps[0]; p.ps1 = ps[1]; p.ps2 = ps[2]; p.ps3 = ps[3];
     const size_t segs = (size_t)B * (C - 1);
     p.counts = (int*)ws;
-    p.keys = (u64*)((char*)ws + align_up(segs * sizeof(int), 256));
+    p.thr = (float*)((char*)ws + align_up(segs * sizeof(int), 256));
+    p.keys = (u64*)((char*)ws + 2 * align_up(segs * sizeof(int), 256));
+    p.boxes = (float4*)(p.keys + segs * (size_t)h->tab.N);
     p.cap = h->tab.N;
     p.num_tiles = (long long)toff * B;
+    RONK_REQUIRE(p.num_tiles < (1ll << 31), RONK_ELIMIT, "ronk_decode_select_topk: too many tiles (B * anchors)");
     p.out_scores = out_scores;
     p.out_boxes = (float4*)out_boxes;
     p.out_idx = out_idx;
     cudaStream_t st = (cudaStream_t)stream;
 
-    zero_i32_kernel<<<(unsigned)((segs + 255) / 256), 256, 0, st>>>(p.counts, segs);
+    init_segments_kernel<<<(unsigned)((segs + 255) / 256), 256, 0, st>>>(p.counts, p.thr, p.sel_thr, segs);
     RONK_LAUNCHED();
 
     const int stage_floats = (kTileRows * C + 4 + 3) & ~3;
-    size_t smem_a = (size_t)2 * stage_floats * 4 + (size_t)16 * (C - 1) * 4;
+    size_t smem_a = (size_t)2 * ((size_t)stage_floats * 4 + kTileRows * 16);
     RONK_REQUIRE(smem_a <= 220 * 1024, RONK_ELIMIT, "ronk_decode_select_topk: C too large for the shared-memory tile");
     if (smem_a > 48 * 1024)
         RONK_CUDA(cudaFuncSetAttribute(scatter_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    int per_sm = (int)((220 * 1024) / (smem_a + 1024));
+    int per_sm = (int)((220 * 1024) / (smem_a + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     long long grid = (long long)h->num_sms * per_sm;
@@ -428,7 +764,7 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
 
     int P = 1;
     while (P < K) P <<= 1;
-    size_t smem_b = (size_t)(P + kStageKeys) * sizeof(u64);
+    size_t smem_b = (size_t)(P + kListCap) * sizeof(u64) + (size_t)kBins * sizeof(unsigned);
     if (smem_b > 48 * 1024)
         RONK_CUDA(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     select_topk_kernel<<<(unsigned)segs, kTopkThreads, smem_b, st>>>(p);
