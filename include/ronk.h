@@ -51,6 +51,9 @@ extern "C" {
 #define RONK_SELECT_DEFAULT 0
 #define RONK_SELECT_LOC_DECODED 1        /* loc_layers already hold decoded boxes (the reference's
                                             detected_bboxes receives bboxes_decode's output) */
+#define RONK_SELECT_NO_SAMPLING 2        /* one scatter pass with select_threshold only (no sampled pivot) */
+#define RONK_SELECT_TEST_REBUILD 4       /* test hook: pivot = highest sampled score and every pivoted
+                                            (image, class) takes the exact list-rebuild path */
 
 typedef struct ronk_anchors ronk_anchors_t;
 

@@ -10,7 +10,7 @@ RONK_OK, RONK_EINVAL, RONK_ECUDA, RONK_ENOMEM, RONK_ELIMIT = 0, -1, -2, -3, -4
 KIND_RON, KIND_SSD = 0, 1
 NMS_MIN, NMS_UNION = 0, 1
 MATCH_NO_IGNORE_BETWEEN, MATCH_NO_GT_MAX_FIRST = 1, 2
-SELECT_LOC_DECODED = 1
+SELECT_LOC_DECODED, SELECT_NO_SAMPLING, SELECT_TEST_REBUILD = 1, 2, 4
 
 c_void_p, c_int, c_float, c_double, c_size_t, c_longlong = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t, ctypes.c_longlong)

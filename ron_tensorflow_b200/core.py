@@ -262,7 +262,7 @@ def _layer_ptrs(anchors, tensors, last, what):
 
 def decode_select_topk(anchors, loc_layers, cls_layers, obj_layers=None, objectness_threshold=0.0,
                        select_threshold=None, clip=None, min_size=None, top_k=400, prior_scaling=_PS,
-                       loc_is_decoded=False, want_idx=False):
+                       loc_is_decoded=False, want_idx=False, sampling=True, _test_rebuild=False):
     """Fused decode + objectness gate + select + clip + min-size + per-class top-k
     (ronk_decode_select_topk).  Returns scores [B,C-1,K], boxes [B,C-1,K,4], idx [B,C-1,K] or None."""
     dev = anchors.device
@@ -287,7 +287,9 @@ def decode_select_topk(anchors, loc_layers, cls_layers, obj_layers=None, objectn
         rc = L.ronk_decode_select_topk(
             anchors.handle, loc_p, cls_p, obj_p, B, C, float(objectness_threshold), sel,
             _ffi.farr(clip) if clip is not None else None, -1.0 if min_size is None else float(min_size),
-            _ffi.farr(prior_scaling), K, _ffi.SELECT_LOC_DECODED if loc_is_decoded else 0,
+            _ffi.farr(prior_scaling), K,
+            (_ffi.SELECT_LOC_DECODED if loc_is_decoded else 0) | (0 if sampling else _ffi.SELECT_NO_SAMPLING) |
+            (_ffi.SELECT_TEST_REBUILD if _test_rebuild else 0),
             _ptr(scores), _ptr(boxes), _ptr(idx), _ptr(ws), _stream())
     _ffi.check(rc)
     del loc_t, cls_t, obj_t

@@ -80,17 +80,33 @@ nms_kernel(const __grid_constant__ NmsParams p) {
             score = p.scores[in0 + pos];
         }
         const float vol = (box.w - box.y) * (box.z - box.x);
-        // 1. against everything kept by earlier chunks (broadcast reads; no loop-carried branch)
+        // 1. against everything kept by earlier chunks (broadcast reads).  Branch-free fast test: the
+        //    sign of inner - thr * den decides unless it is within 1e-6 relative of zero (then, or for
+        //    NaNs, the chunk is redone with the exact division below).
         bool dead = !valid;
+        bool unclear = false;
         for (int i0 = 0; i0 < count; i0 += 8) {
             const int lim = min(8, count - i0);
 #pragma unroll 4
             for (int i = 0; i < lim; ++i) {
-                float4 kb = s_kbox[i0 + i];
-                float kv = s_kvol[i0 + i];
-                dead |= suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp);
+                const float4 kb = s_kbox[i0 + i];
+                const float kv = s_kvol[i0 + i];
+                const float h = fmaxf(fminf(box.z, kb.z) - fmaxf(box.x, kb.x), 0.f);
+                const float w = fmaxf(fminf(box.w, kb.w) - fmaxf(box.y, kb.y), 0.f);
+                const float inner = h * w;
+                const float den = (p.mode == RONK_NMS_UNION) ? ((vol - inner) + kv) : fminf(vol, kv);
+                const float t = p.thr * den;
+                const float d = inner - t;
+                const bool pos = den > 0.f;                       // else safe_divide gives overlap 0
+                dead |= pos ? (d > 0.f) : zero_supp;
+                unclear |= pos && !(fabsf(d) > t * 1e-6f);
             }
             if (__all_sync(full, dead)) break;
+        }
+        if (__any_sync(full, unclear && valid)) {
+            dead = !valid;
+            for (int i = 0; i < count; ++i)
+                dead |= suppresses(box, vol, s_kbox[i], s_kvol[i], p.mode, p.thr, zero_supp);
         }
         // 2. inside the chunk: walk the survivors in order; each one that is still alive is kept
         //    and kills the later lanes it overlaps

@@ -13,6 +13,8 @@
 //     per-(image, class) candidate lists with warp-ballot + one global atomic per class per CTA.
 //   select_topk_kernel         one CTA per (image, class): exact radix select of the top K keys,
 //     bitonic sort, box re-decode of the K winners.
+#include <math.h>
+
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -37,6 +39,11 @@ struct PostParams {
     float4* boxes;                   // [B, N] final (decoded, clipped) box of every surviving anchor
     int cap;
     long long num_tiles;
+    // tile subset of this scatter launch: permuted tile index r' in [r_lo, r_hi) of every image,
+    // actual tile r = (r' * perm_mul) % tiles_per_image (perm_mul coprime: an even spread)
+    int r_lo, r_hi, perm_mul;
+    int force_rebuild;               // test hook: always take the exact-rebuild path of pivoted segments
+    int pivot_rank;                  // rank (from the top) of the sampled key that becomes the pivot; 0 = no sampling
     float* out_scores;
     float4* out_boxes;
     int* out_idx;
@@ -100,99 +107,46 @@ __device__ __forceinline__ TileInfo tile_info(const PostParams& p, int b, int r)
 
 constexpr int kScatWarps = kTileRows / 32;
 
-// Class-major scan of one tile by one warp (slow, fully general form: used for the few tiles
-// whose last <= 3 score words are not covered by the 16-byte granular bulk copy and must be read
-// from global memory).  One atomic per (class, chunk of 32 surviving rows).
-__device__ __noinline__ void class_scan_tail(const PostParams& p, const TileInfo& t, const float* s_cls,
-                                             const int* s_rows, const unsigned* s_vmask, int n_gated, int nchunks) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = p.C;
-    const int wlim = (int)(t.a1 - t.start_w);   // words of this tile that sit in smem
-    const float* gcls = p.cls[t.layer] + t.start_w;
-    const unsigned nkey0 = 0xffffffffu - (unsigned)(p.tab.offs[t.layer] + t.t0);
-    for (int c = 1 + warp; c < C; c += kScatWarps) {
-        int* cnt = p.counts + (size_t)t.b * (C - 1) + (c - 1);
-        u64* dst = p.keys + ((size_t)t.b * (C - 1) + (c - 1)) * p.cap;
-        for (int k = 0; k < nchunks; ++k) {
-            const int i = k * 32 + lane;
-            bool pass = false;
-            float v = 0.f;
-            int r = 0;
-            if (i < n_gated && ((s_vmask[k] >> lane) & 1u)) {
-                r = s_rows[i];
-                const int e = r * C + c;
-                v = (e < wlim) ? s_cls[e] : gcls[e];
-                pass = v > p.thr[(size_t)t.b * (C - 1) + (c - 1)];
-            }
-            const unsigned m = __ballot_sync(full, pass);
-            if (m == 0u) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(cnt, __popc(m));
-            base = __shfl_sync(full, base, 0);
-            if (pass) dst[base + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(v) << 32) | (u64)(nkey0 - (unsigned)r);
-        }
-    }
-}
-
-// Fast form, NCH = number of 32-row chunks of surviving rows (compile-time, so the per-lane row
-// state lives in registers).  Per group of up to 32 classes of this warp: pass 1 counts the passing
-// rows of every class (ballots only), then lane j reserves class j's slots -- all atomics of the
-// group are in flight together, one round trip -- and pass 2 writes the u64 keys.
-template <int NCH>
+// Class scan of one tile: lane = class, warp w walks every 8th surviving valid row.  The class
+// threshold sits in a register, a row's scores are consecutive words of shared memory (no bank
+// conflict), and nothing has to be ordered -- keys of one (image, class) list may land in any order,
+// they are sorted later -- so there are no ballots or prefix sums: pass 1 counts per lane, ONE
+// atomic per lane reserves the slots of all (up to 32) classes at once, pass 2 stores the u64 keys
+// (score bits << 32 | ~anchor).  TAIL: the last <= 3 score words of a layer array are not covered by
+// the 16-byte granular bulk copy and are read from global memory.
+template <bool TAIL>
 __device__ __forceinline__ void class_scan(const PostParams& p, const TileInfo& t, const float* s_cls,
-                                           const int* s_rows, const unsigned* s_vmask, int n_gated) {
-    const unsigned full = 0xffffffffu;
+                                           const int* s_vrows, int nslots) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = p.C, CM = p.C - 1;
     const unsigned nkey0 = 0xffffffffu - (unsigned)(p.tab.offs[t.layer] + t.t0);
-    const unsigned lt = (1u << lane) - 1u;
-    const float* row[NCH];      // this lane's surviving row of chunk k (scores), or the tile start when none
-    unsigned nk[NCH];           // low word of the key
-    unsigned ok = 0u;           // bit k: this lane has a valid surviving row in chunk k
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-        const int i = k * 32 + lane;
-        int r = 0;
-        if (i < n_gated && ((s_vmask[k] >> lane) & 1u)) {
-            r = s_rows[i];
-            ok |= 1u << k;
-        }
-        row[k] = s_cls + r * C;
-        nk[k] = nkey0 - (unsigned)r;
-    }
+    const int wlim = (int)(t.a1 - t.start_w);   // words of this tile that sit in smem
+    const float* gcls = p.cls[t.layer] + t.start_w;
     const size_t seg0 = (size_t)t.b * CM;
-    for (int c0 = 1 + warp; c0 < C; c0 += 32 * kScatWarps) {
-        // ---- pass 1: totals (lane j keeps the total of class c0 + 8 j)
-        int mytotal = 0;
-        int j = 0;
-        for (int c = c0; c < C && j < 32; c += kScatWarps, ++j) {
-            const float thr = p.thr[seg0 + (c - 1)];
-            int total = 0;
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const bool pass = ((ok >> k) & 1u) && row[k][c] > thr;
-                total += __popc(__ballot_sync(full, pass));
-            }
-            if (lane == j) mytotal = total;
+    for (int cb = 0; cb < CM; cb += 32) {
+        const bool act = cb + lane < CM;
+        const int ci = act ? cb + lane : 0;
+        const float thr = act ? p.thr[seg0 + ci] : __int_as_float(0x7f800000);
+        const float* col = s_cls + 1 + ci;
+        int cnt = 0;
+        for (int j = warp; j < nslots; j += kScatWarps) {
+            const int r = s_vrows[j];                  // warp-uniform; -1 = empty slot
+            if (r < 0) continue;
+            const int e = r * C;
+            const float v = (!TAIL || e + 1 + ci < wlim) ? col[e] : gcls[e + 1 + ci];
+            cnt += (v > thr) ? 1 : 0;
         }
-        const int myc = c0 + lane * kScatWarps;
-        int mybase = 0;
-        if (mytotal > 0) mybase = atomicAdd(p.counts + seg0 + (myc - 1), mytotal);
-        // ---- pass 2: keys
-        j = 0;
-        for (int c = c0; c < C && j < 32; c += kScatWarps, ++j) {
-            int pos = __shfl_sync(full, mybase, j);
-            if (__shfl_sync(full, mytotal, j) == 0) continue;
-            const float thr = p.thr[seg0 + (c - 1)];
-            u64* dst = p.keys + (seg0 + (c - 1)) * p.cap;
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const float v = row[k][c];
-                const bool pass = ((ok >> k) & 1u) && v > thr;
-                const unsigned m = __ballot_sync(full, pass);
-                if (pass) dst[pos + __popc(m & lt)] = ((u64)__float_as_uint(v) << 32) | (u64)nk[k];
-                pos += __popc(m);
+        if (cnt == 0) continue;
+        u64* dst = p.keys + (seg0 + ci) * p.cap;
+        int pos = atomicAdd(p.counts + seg0 + ci, cnt);
+        for (int j = warp; j < nslots; j += kScatWarps) {
+            const int r = s_vrows[j];
+            if (r < 0) continue;
+            const int e = r * C;
+            const float v = (!TAIL || e + 1 + ci < wlim) ? col[e] : gcls[e + 1 + ci];
+            if (v > thr) {
+                dst[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(nkey0 - (unsigned)r);
+                ++pos;
             }
         }
     }
@@ -204,7 +158,7 @@ __device__ __forceinline__ void class_scan(const PostParams& p, const TileInfo& 
 //  B. one thread per SURVIVING row decodes + clips + size-tests the box (two float64 exp) from the
 //     localisation rows that arrived with the same TMA transaction as the scores, and stores the
 //     box to the per-image box table (the top-k kernel gathers its winners from it);
-//  C. class-major scan (class_scan above): warp w owns classes 1+w, 1+w+8, ...
+//  C. class scan (class_scan above): lane = class, the 8 warps share the surviving valid rows.
 __global__ void __launch_bounds__(kTileRows, 4)
 scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -214,7 +168,7 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     __shared__ __align__(8) u64 s_bar[2];
     __shared__ int s_rows[kTileRows];
     __shared__ int s_wcnt[kScatWarps];
-    __shared__ unsigned s_vmask[kScatWarps];
+    __shared__ int s_vrows[kTileRows];      // surviving rows with a valid box, compacted inside each 32-row chunk; -1 = empty
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
@@ -243,10 +197,11 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
 
     // tiles are visited grid-stride; (b, r) = (image, tile inside the image) advances without divisions
     const int tpi = p.tile_off[p.tab.L];
-    const int step_b = (int)(gridDim.x / (unsigned)tpi), step_r = (int)(gridDim.x % (unsigned)tpi);
-    int b = (int)(blockIdx.x / (unsigned)tpi), r = (int)(blockIdx.x % (unsigned)tpi);
+    const int cnt = p.r_hi - p.r_lo;                    // tiles of this launch per image
+    const int step_b = (int)(gridDim.x / (unsigned)cnt), step_r = (int)(gridDim.x % (unsigned)cnt);
+    int b = (int)(blockIdx.x / (unsigned)cnt), r = (int)(blockIdx.x % (unsigned)cnt);
     if (b >= p.B) return;
-    TileInfo t = tile_info(p, b, r);
+    TileInfo t = tile_info(p, b, (int)(((unsigned)(p.r_lo + r) * (unsigned)p.perm_mul) % (unsigned)tpi));
     if (tid == 0) issue(t, 0);
     bool gate = load_gate(t);
     unsigned phase = 0u;   // bit st = parity the next wait on stage st must see
@@ -254,11 +209,11 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         const int st = it & 1;
         // prefetch the next tile into the other stage (freed by the barrier that ended iteration it-1)
         int nb = b + step_b, nr = r + step_r;
-        if (nr >= tpi) { nr -= tpi; ++nb; }
+        if (nr >= cnt) { nr -= cnt; ++nb; }
         TileInfo tn = t;
         bool gate_next = false;
         if (nb < p.B) {
-            tn = tile_info(p, nb, nr);
+            tn = tile_info(p, nb, (int)(((unsigned)(p.r_lo + nr) * (unsigned)p.perm_mul) % (unsigned)tpi));
             if (tid == 0) issue(tn, st ^ 1);
             gate_next = load_gate(tn);          // objectness of the next tile: the load overlaps this tile's work
         }
@@ -287,8 +242,9 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         // ---- B. boxes of the surviving rows (compacted: thread i <-> row s_rows[i])
         if (warp < nchunks) {
             bool valid = false;
+            int rr = 0;
             if (tid < n_gated) {
-                const int rr = s_rows[tid];
+                rr = s_rows[tid];
                 const int n = p.tab.offs[t.layer] + t.t0 + rr;
                 float4 box = p.decoded ? s_loc[rr] : decode_box(s_loc[rr], p.dec[n], p.ps0, p.ps1, p.ps2, p.ps3);
                 if (p.has_clip) box = clip_box(box, p.clip);
@@ -298,30 +254,23 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
                     float w = box.w - box.y;
                     valid = (w > p.min_size) && (h > p.min_size);
                 }
-                if (valid) p.boxes[(size_t)t.b * p.tab.N + n] = box;
+                // invalid rows get a NaN marker: the exact-rebuild path of the top-k kernel reads it
+                const float qn = __int_as_float(0x7fc00000);
+                p.boxes[(size_t)t.b * p.tab.N + n] = valid ? box : make_float4(qn, qn, qn, qn);
             }
             const unsigned vm = __ballot_sync(full, valid);
-            if (lane == 0) s_vmask[warp] = vm;
+            s_vrows[tid] = -1;
+            __syncwarp();
+            if (valid) s_vrows[warp * 32 + __popc(vm & ((1u << lane) - 1u))] = rr;
         }
         __syncthreads();
 
-        // ---- C. class-major scan over the compacted rows
-        if (t.end_w > t.a1) {
-            class_scan_tail(p, t, s_cls, s_rows, s_vmask, n_gated, nchunks);
-        } else {
-            switch (nchunks) {
-                case 0: break;
-                case 1: class_scan<1>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                case 2: class_scan<2>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                case 3: class_scan<3>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                case 4: class_scan<4>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                case 5: class_scan<5>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                case 6: class_scan<6>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                case 7: class_scan<7>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-                default: class_scan<8>(p, t, s_cls, s_rows, s_vmask, n_gated); break;
-            }
-        }
-        __syncthreads();   // stage st, s_rows and s_vmask are free again
+        // ---- C. class scan over the surviving valid rows
+        if (t.end_w > t.a1)
+            class_scan<true>(p, t, s_cls, s_vrows, nchunks * 32);
+        else
+            class_scan<false>(p, t, s_cls, s_vrows, nchunks * 32);
+        __syncthreads();   // stage st, s_rows and s_vrows are free again
         t = tn;
         b = nb;
         r = nr;
@@ -337,8 +286,8 @@ struct ListSrc {
     __device__ __forceinline__ u64 get(int i) const { return i < staged ? s[i] : g[i]; }
 };
 
-constexpr int kListCap = 4096;                               // survivors of the sampling pre-filter (shared memory)
-constexpr int kKeysPerThread = kListCap / kTopkThreads;      // 16
+constexpr int kListCap = 2048;                               // survivors of the sampling pre-filter (shared memory)
+constexpr int kKeysPerThread = kListCap / kTopkThreads;      // 8
 constexpr int kSample = 2 * kTopkThreads;                    // 512 sampled keys
 constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
@@ -505,16 +454,122 @@ __device__ __forceinline__ void block_bitonic_regs(u64* s_sort) {
     __syncthreads();
 }
 
+// Pivot of one (image, class) from the keys of the SAMPLED tiles (first scatter launch), one warp
+// per segment: an 11-bit histogram of the score bits (exponent + 3 mantissa bits) in shared
+// memory, scanned from the top; the pivot is the lower edge of the bin that holds the
+// pivot_rank-th largest sampled score.  pivot_rank = expected number of top-K scores in the sample
+// + 4 sigma + 8, so the second scatter launch (all other tiles, threshold = pivot) keeps every
+// top-K candidate with overwhelming probability; the top-k kernel verifies that and rebuilds the
+// list exactly when it did not.  Any pivot is safe; it only has to be a good guess.
+constexpr int kPivotWarps = 4;
+constexpr int kPivotPad = kBins + (kBins / 64) * 2;      // 2 u16 of padding per 64 bins: lane-private rows hit distinct banks
+__device__ __forceinline__ int pivot_slot(unsigned d) { return (int)(d + ((d >> 6) << 1)); }
+
+__global__ void __launch_bounds__(kPivotWarps * 32)
+pivot_kernel(const __grid_constant__ PostParams p) {
+    __shared__ __align__(16) unsigned short s_h[kPivotWarps][kPivotPad];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t seg = (size_t)blockIdx.x * kPivotWarps + warp;
+    if (seg >= (size_t)p.B * (p.C - 1)) return;
+    int n = p.counts[seg];
+    n = n > p.cap ? p.cap : n;
+    if (n < p.pivot_rank || n > 65535) return;            // too few samples: keep sel_thr
+    unsigned short* h = s_h[warp];
+    for (int i = lane; i < kPivotPad / 2; i += 32) reinterpret_cast<unsigned*>(h)[i] = 0u;
+    __syncwarp();
+    const u64* g = p.keys + seg * p.cap;
+    for (int i0 = 0; i0 < n; i0 += 128) {
+        u64 k[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * 32 + lane;
+            k[q] = (i < n) ? g[i] : 0ull;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool act = k[q] != 0ull;
+            const unsigned d = (unsigned)(k[q] >> 52) & (kBins - 1);     // score bits [30:20]
+            const unsigned amask = __ballot_sync(full, act);
+            if (act) {
+                const unsigned peers = __match_any_sync(amask, d);
+                if (lane == __ffs(peers) - 1) h[pivot_slot(d)] += (unsigned short)__popc(peers);   // one lane per distinct bin
+            }
+            __syncwarp();
+        }
+    }
+    // lane l owns the 64 bins [64 m, 64 m + 63], m = 31 - l (descending over lanes); its 32 words are
+    // contiguous and start in bank m
+    const int m = 31 - lane;
+    const unsigned* hw = reinterpret_cast<const unsigned*>(h) + 33 * m;
+    unsigned sum = 0;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+        const unsigned w = hw[q];
+        sum += (w & 0xffffu) + (w >> 16);
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += v;
+    }
+    unsigned above = incl - sum;
+    const unsigned need = (unsigned)p.pivot_rank;
+    if (above < need && need <= above + sum) {
+        int bin = 64 * m + 63;
+        for (; bin > 64 * m; --bin) {
+            above += h[pivot_slot((unsigned)bin)];
+            if (above >= need) break;
+        }
+        // scatter passes v > thr: everything in the pivot bin and above must pass
+        const unsigned lower = (unsigned)bin << 20;
+        const float thr = __uint_as_float(lower - 1u);
+        if (thr > p.sel_thr) p.thr[seg] = thr;
+    }
+}
+
+// Exact rebuild of one (image, class) list straight from the inputs (the sampled pivot turned out
+// too high, probability ~1e-4 per segment): objectness gate, box validity from the box table's NaN
+// marker, score > sel_thr.  Returns the new length (block-uniform).
+__device__ int rebuild_list(const PostParams& p, int b, int c, u64* g, int* s_cnt) {
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+    for (int l = 0; l < p.tab.L; ++l) {
+        const int n_l = p.tab.offs[l + 1] - p.tab.offs[l];
+        for (int i0 = 0; i0 < n_l; i0 += kTopkThreads) {
+            const int i = i0 + tid;
+            bool sel = false;
+            float v = 0.f;
+            if (i < n_l) {
+                const size_t row = (size_t)b * n_l + i;
+                bool gate = true;
+                if (p.has_obj) gate = p.obj[l][row] > p.obj_thr;
+                if (gate) {
+                    const float bx = p.boxes[(size_t)b * p.tab.N + p.tab.offs[l] + i].x;
+                    v = p.cls[l][row * p.C + c];
+                    sel = (bx == bx) && v > p.sel_thr;
+                }
+            }
+            warp_append(sel, ((u64)__float_as_uint(v) << 32) | (u64)(0xffffffffu - (unsigned)(p.tab.offs[l] + i)), g,
+                        p.cap, s_cnt);
+        }
+    }
+    __syncthreads();
+    return *s_cnt;
+}
+
 // One CTA per (image, class): exact top-K of the candidate list, sorted descending
 // (tf.nn.top_k order: lower anchor first among equal scores), boxes gathered from the box table.
 //   n <= K            every key is a winner;
-//   n <= 4096         keys in registers, radix select of the K-th key;
+//   n <= 2048         keys in registers, radix select of the K-th key;
 //   longer lists      a strided sample of 512 keys gives a pivot that is below the K-th key with
 //                     overwhelming probability (rank = expected + 4 sigma + 8); one streaming pass keeps
 //                     the keys >= pivot in shared memory, and the select runs on those.  If the pivot
-//                     turns out too high (fewer than K survivors) or too low (more than 4096), the
+//                     turns out too high (fewer than K survivors) or too low (more than 2048), the
 //                     generic 8-bit radix select over the whole list takes over -- always exact.
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __launch_bounds__(kTopkThreads, 4)
 select_topk_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = next_pow2(p.K);
@@ -529,7 +584,9 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
     const int b = seg / CM;
     int n = p.counts[seg];
     n = n > p.cap ? p.cap : n;
-    const u64* g = p.keys + (size_t)seg * p.cap;
+    u64* g = p.keys + (size_t)seg * p.cap;
+    const float seg_thr = p.thr[seg];
+    for (int attempt = 0;; ++attempt) {
     for (int i = tid; i < P; i += kTopkThreads) s_sort[i] = 0ull;
     if (tid == 0) { s_cnt = 0; s_ctl[3] = 0; }
     __syncthreads();
@@ -594,6 +651,15 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
         else if (P == 2 * kTopkThreads) block_bitonic_regs<2>(s_sort);
         else if (P == 4 * kTopkThreads) block_bitonic_regs<4>(s_sort);
         else block_bitonic_desc(s_sort, P);
+    }
+    // exact iff no pivot was used, or the K-th winner is above the pivot (every candidate above the
+    // pivot is in the list).  Otherwise rebuild the list from the inputs and select again.
+    if (attempt > 0 || !(seg_thr > p.sel_thr)) break;
+    const u64 kth = s_sort[p.K - 1];
+    if (kth != 0ull && __uint_as_float((unsigned)(kth >> 32)) > seg_thr && !p.force_rebuild) break;
+    __syncthreads();
+    n = rebuild_list(p, b, seg - b * CM + 1, g, &s_cnt);
+    n = n > p.cap ? p.cap : n;
     }
     for (int r = tid; r < p.K; r += kTopkThreads) {
         u64 k = s_sort[r];
@@ -757,10 +823,53 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     int per_sm = (int)((220 * 1024) / (smem_a + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    long long grid = (long long)h->num_sms * per_sm;
-    if (grid > p.num_tiles) grid = p.num_tiles;
-    scatter_candidates_kernel<<<(unsigned)grid, kTileRows, smem_a, st>>>(p);
-    RONK_LAUNCHED();
+    // Two scatter launches when the lists would be much longer than K: first a spread-out eighth of
+    // every image's tiles (threshold sel_thr), then a per-(image, class) pivot from those keys,
+    // then all other tiles with the pivot as threshold.  perm_mul ~ 0.618 * tiles, coprime.
+    const int tpi = toff;
+    int tpi1 = 0;
+    p.perm_mul = 1;
+    p.pivot_rank = 0;
+    p.force_rebuild = (select_flags & RONK_SELECT_TEST_REBUILD) ? 1 : 0;
+    if (!(select_flags & RONK_SELECT_NO_SAMPLING) && tpi >= 16 && (long long)K * 8 <= h->tab.N) {
+        tpi1 = tpi / 8;
+        if (tpi1 > 16) tpi1 = 16;
+        int m = (int)(0.618 * tpi);
+        auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+        while (m < tpi && gcd(m, tpi) != 1) ++m;
+        if (m >= tpi) m = 1;
+        p.perm_mul = m;
+        long long rows = 0;
+        for (int q = 0; q < tpi1; ++q) {
+            int r = (int)(((long long)q * m) % tpi);
+            int l = 0;
+            while (l + 1 < h->tab.L && r >= p.tile_off[l + 1]) ++l;
+            int n_l = h->tab.offs[l + 1] - h->tab.offs[l];
+            int t0 = (r - p.tile_off[l]) * kTileRows;
+            rows += (n_l - t0 < kTileRows) ? (n_l - t0) : kTileRows;
+        }
+        const double mu = (double)K * (double)rows / (double)h->tab.N;
+        p.pivot_rank = (int)(mu + 4.0 * sqrt(mu) + 8.0);
+        if (p.force_rebuild) p.pivot_rank = 1;       // pivot = the highest sampled score: (almost) always too high
+    }
+    auto launch_scatter = [&](int r_lo, int r_hi) -> int {
+        p.r_lo = r_lo;
+        p.r_hi = r_hi;
+        long long tiles = (long long)(r_hi - r_lo) * B;
+        long long grid = (long long)h->num_sms * per_sm;
+        if (grid > tiles) grid = tiles;
+        scatter_candidates_kernel<<<(unsigned)grid, kTileRows, smem_a, st>>>(p);
+        RONK_LAUNCHED();
+        return RONK_OK;
+    };
+    if (tpi1 > 0) {
+        if (int rc = launch_scatter(0, tpi1)) return rc;
+        pivot_kernel<<<(unsigned)((segs + kPivotWarps - 1) / kPivotWarps), kPivotWarps * 32, 0, st>>>(p);
+        RONK_LAUNCHED();
+        if (int rc = launch_scatter(tpi1, tpi)) return rc;
+    } else {
+        if (int rc = launch_scatter(0, tpi)) return rc;
+    }
 
     int P = 1;
     while (P < K) P <<= 1;

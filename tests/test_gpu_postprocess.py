@@ -243,3 +243,25 @@ def test_fine_grained_functions(golden):
         eq(d_s[c], pred[:, :, c] * m, 'select scores')
         eq(d_b[c], loc * m[..., None], 'select boxes')
     assert 0 not in d_s and len(d_s) == 20
+
+
+@pytest.mark.parametrize('path', ['sampled', 'unsampled', 'rebuild'])
+@pytest.mark.parametrize('dense,K', [(False, 400), (True, 400), (False, 64), (True, 1500)])
+def test_topk_paths_vs_oracle(ron, dec_anchors, path, dense, K):
+    """The three ways the top-k kernel can arrive at its list -- sampled pivot + second scatter
+    launch, one plain scatter launch, and the exact rebuild after a (forced) too-high pivot --
+    must give the oracle's scores / anchor indices / boxes bit for bit."""
+    from ron_tensorflow_b200 import core
+    net, anchors = ron
+    B = 2
+    loc, pred, obj = synth.make_predictions(311 + int(dense) + K, B, 21250, 21, hot=300, dense=dense)
+    s, bx, ix = core.decode_select_topk(anchors.anchor_set, _layers(loc, False), _layers(pred, False), _layers(obj, False),
+                                        0.03, 0.01, [0., 0., 1., 1.], 0.03, K, want_idx=True,
+                                        sampling=(path != 'unsampled'), _test_rebuild=(path == 'rebuild'))
+    for b in range(B):
+        boxes = O.decode(loc[b], dec_anchors)
+        gate = (obj[b] > np.float32(0.03)).astype(np.float32)
+        os_, ob, oi = O.select_topk_image(gate[:, None] * pred[b], boxes, 0.01, K, [0., 0., 1., 1.], 0.03)
+        eq(ix[b], oi, 'anchor idx b=%d' % b)
+        eq(s[b], os_, 'scores b=%d' % b)
+        eq(bx[b], ob, 'boxes b=%d' % b)
