@@ -110,6 +110,46 @@ cudaError_t finish_compaction(ronk_anchors* h) {
     if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_inside_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cidx, cidx.data(), (size_t)N * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_ccor, ccor.data(), ccor.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+
+    // ---- work-item tables (see common.cuh).  A set of 64 consecutive inside anchors is "heavy" when its
+    // bounding extent, clipped to the image, covers more than 40 % of it: then nearly every GT box
+    // survives the cull and the item is as long as the GT list.
+    const int Nin = h->n_inside;
+    const int nsets = (Nin + 63) / 64;
+    std::vector<char> heavy(nsets > 0 ? nsets : 1, 0);
+    for (int sidx = 0; sidx < nsets; ++sidx) {
+        float y0 = 1e30f, x0 = 1e30f, y1 = -1e30f, x1 = -1e30f;
+        for (int c = sidx * 64; c < Nin && c < sidx * 64 + 64; ++c) {
+            y0 = fminf(y0, ccor[(size_t)c * 4 + 0]); x0 = fminf(x0, ccor[(size_t)c * 4 + 1]);
+            y1 = fmaxf(y1, ccor[(size_t)c * 4 + 2]); x1 = fmaxf(x1, ccor[(size_t)c * 4 + 3]);
+        }
+        float hh = fminf(y1, 1.f) - fmaxf(y0, 0.f), ww = fminf(x1, 1.f) - fmaxf(x0, 0.f);
+        heavy[sidx] = (hh > 0.f && ww > 0.f && hh * ww > 0.4f) ? 1 : 0;
+    }
+    auto flat_lo = [&](int c0) { return c0 == 0 ? 0 : idx[c0]; };
+    auto flat_hi = [&](int c1) { return c1 >= Nin ? N : idx[c1]; };
+    for (int t = 0; t < 3; ++t) {
+        std::vector<int> items;
+        for (int s0 = 0; s0 < (nsets > 0 ? nsets : 1); s0 += 4) {
+            int nh = 0;
+            for (int q = s0; q < s0 + 4 && q < nsets; ++q) nh += heavy[q];
+            const bool cut = (t == 2) || (t == 1 && nh >= 2);
+            if (cut) {
+                for (int q = s0; q < s0 + 4 && q < (nsets > 0 ? nsets : 1); ++q) {
+                    int c0 = q * 64, c1 = c0 + 64;
+                    items.insert(items.end(), {c0, flat_lo(c0), flat_hi(c1), 4});
+                }
+            } else {
+                int c0 = s0 * 64, c1 = c0 + 256;
+                items.insert(items.end(), {c0, flat_lo(c0), flat_hi(c1), 1});
+            }
+        }
+        h->n_items[t] = (int)(items.size() / 4);
+        e = cudaMalloc(&h->d_items[t], items.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_items[t], items.data(), items.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
     return e;
 }
 
@@ -291,6 +331,8 @@ extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
     if (h->d_inside_idx) cudaFree(h->d_inside_idx);
     if (h->d_cidx) cudaFree(h->d_cidx);
     if (h->d_ccor) cudaFree(h->d_ccor);
+    for (int t = 0; t < 3; ++t)
+        if (h->d_items[t]) cudaFree(h->d_items[t]);
     delete h;
 }
 

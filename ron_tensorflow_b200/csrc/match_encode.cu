@@ -33,8 +33,6 @@
 
 namespace ronk {
 
-constexpr int kEncThreads = 128;
-constexpr int kEncWarps = kEncThreads / 32;
 constexpr int kEncApt = 2;                              // anchors per lane
 constexpr int kEncSet = 32 * kEncApt;                   // anchors per warp-set
 
@@ -46,6 +44,7 @@ struct EncodeParams {
     const float4* enc;        // [N]   (cy, cx, h', w')
     const uint8_t* inside;    // [N]
     int N, Nin, tiles, anchors_nice;
+    const int4* items;        // [tiles] work items {first compact anchor, first flat anchor, end flat anchor, GT split}
     const float4* gt_boxes;
     const long long* gt_labels;
     const int* gt_counts;
@@ -78,12 +77,21 @@ __device__ __forceinline__ float4 encode_loc(float4 gb, float4 e, const EncodePa
 }
 
 // branch-free IoU in exactly the reference's op order (ssd_common.py:34-47).
-// NICE: every coordinate is 0 or has a magnitude in [2^-15, 2^15] (checked per anchor handle and
-// per image), so the quotient takes the inline division sequence; otherwise IEEE div.rn.
+// NICE: every coordinate is 0 or has a magnitude in [2^-15, 2^15] and no GT side exceeds 1 (checked
+// per anchor handle and per image), so the quotient takes the inline division sequence and the
+// clamps are saturating subtracts; otherwise IEEE div.rn and fmaxf.
 template <bool NICE>
 __device__ __forceinline__ float iou_ref(float4 t, float ga, float4 a, float aa) {
-    float h = fmaxf(fminf(t.z, a.z) - fmaxf(t.x, a.x), 0.f);
-    float w = fmaxf(fminf(t.w, a.w) - fmaxf(t.y, a.y), 0.f);
+    float h, w;
+    if (NICE) {
+        // max(d, 0) as a saturating subtract (one FMA-pipe instruction instead of FADD + FMNMX):
+        // exact because d <= the GT side <= 1 (checked per image)
+        h = __saturatef(fminf(t.z, a.z) - fmaxf(t.x, a.x));
+        w = __saturatef(fminf(t.w, a.w) - fmaxf(t.y, a.y));
+    } else {
+        h = fmaxf(fminf(t.z, a.z) - fmaxf(t.x, a.x), 0.f);
+        w = fmaxf(fminf(t.w, a.w) - fmaxf(t.y, a.y), 0.f);
+    }
     float inter = h * w;
     float uni = (ga + aa) - inter;
     // where(union == 0, 0, inter / union); union == 0 implies inter == 0
@@ -99,9 +107,10 @@ __device__ __forceinline__ bool nice_coord(float v) {
 // Per image, run by the CTA that finished the image last: g2a[g] = decoded per-GT best anchor
 // (all-zero row -> anchor 0); the lowest GT index that claims an anchor wins; score =
 // overlap[g, n].  Also restores the workspace to zero for the next call.
+template <int NT>
 __device__ void force_image(const EncodeParams& p, int b, int G, int* s_n, int* s_cl) {
     const int tid = threadIdx.x;
-    for (int g = tid; g < p.Gmax; g += kEncThreads) {
+    for (int g = tid; g < p.Gmax; g += NT) {
         size_t o = (size_t)b * p.Gmax + g;
         u64 key = __ldcg(p.ws_keys + o);
         int n = 0;
@@ -113,12 +122,12 @@ __device__ void force_image(const EncodeParams& p, int b, int G, int* s_n, int* 
     }
     if (tid == 0) p.ws_count[b] = 0u;
     __syncthreads();
-    for (int g0 = 0; g0 < G; g0 += kEncThreads) {
+    for (int g0 = 0; g0 < G; g0 += NT) {
         const int g = g0 + tid;
         const bool act = g < G;
         const int n = act ? s_n[g] : -1;
         bool first = act && !s_cl[act ? g : 0];   // gt_max_first=False: a GT that already owns an anchor forces nothing
-        const int lim = min(G, g0 + kEncThreads);
+        const int lim = min(G, g0 + NT);
         for (int g2 = 0; g2 < lim; ++g2) first = first && !(g2 < g && s_n[g2] == n && !s_cl[g2]);
         if (!first) continue;
         const float4 gb = p.gt_boxes[(size_t)b * p.Gmax + g];
@@ -206,15 +215,21 @@ __device__ __forceinline__ void sweep(const float4* s_box, const float* s_area, 
     }
 }
 
+constexpr int kEncThreads = 128;
+constexpr int kEncPrefetch = 4;     // flat anchors per thread whose compact index is fetched before the sweep
+
+// One work item: SETS sets of 64 inside anchors starting at compact index c0, GT list cut in SPLIT
+// parts (SETS * SPLIT = 4 warps); writes the outputs of the flat anchors [n_lo, n_hi).
 template <int SETS, int SPLIT>
-__global__ void __launch_bounds__(kEncThreads, 10)
-match_encode_kernel(const __grid_constant__ EncodeParams p) {
-    static_assert(SETS * SPLIT == kEncWarps, "4 warps per CTA");
+__device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char* smem, int b, int c0, int n_lo,
+                                            int n_hi) {
+    static_assert(SETS * SPLIT * 32 == kEncThreads, "4 warps per CTA");
     constexpr int kTile = SETS * kEncSet;
-    extern __shared__ __align__(128) unsigned char smem[];
     float4* s_box = reinterpret_cast<float4*>(smem);              // [gcap] GT corners
     u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [gcap] per-GT (iou bits, ~compact anchor) of this tile
-    float* s_area = reinterpret_cast<float*>(s_best + p.gcap);    // [gcap]
+    u64* s_init = s_best + p.gcap;                                // [gcap] image-wide best when this tile started
+    long long* s_lab = reinterpret_cast<long long*>(s_init + p.gcap);   // [gcap] GT labels
+    float* s_area = reinterpret_cast<float*>(s_lab + p.gcap);     // [gcap]
     __shared__ float s_mv[SPLIT][kTile];                          // per-anchor max overlap, per GT part
     __shared__ int s_mg[SPLIT][kTile];                            // per-anchor first argmax (-1: none)
     __shared__ int s_last;
@@ -222,131 +237,163 @@ match_encode_kernel(const __grid_constant__ EncodeParams p) {
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int set = warp / SPLIT, part = warp % SPLIT;
-    const int b = blockIdx.x;
     const float4* gtb = p.gt_boxes + (size_t)b * p.Gmax;
+    const long long* gtl = p.gt_labels + (size_t)b * p.Gmax;
+    const u64* wsk = p.ws_keys + (size_t)b * p.Gmax;
+    // Every load whose address does not depend on another load is issued here, up front: the first GT
+    // slot of each thread (before the GT count is known), the image-wide bests, this lane's anchors and
+    // the compact indices of the first flat anchors it will write.  One global round trip instead of
+    // four on the critical path of every CTA.
+    const bool spec = tid < p.Gmax;
+    const float4 v_spec = spec ? gtb[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long l_spec = spec ? gtl[tid] : 0ll;
+    const u64 k_spec = spec ? __ldcg(wsk + tid) : 0ull;
+    int cpre[kEncPrefetch];
+#pragma unroll
+    for (int q = 0; q < kEncPrefetch; ++q) {
+        const int n = n_lo + q * kEncThreads + tid;
+        cpre[q] = (n < n_hi) ? p.cidx[n] : -1;
+    }
+    const int set_c0 = c0 + set * kEncSet;
+    float4 a[kEncApt];
+    float area[kEncApt];
+    float wy0 = CUDART_INF_F, wx0 = CUDART_INF_F, wy1 = -CUDART_INF_F, wx1 = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < kEncApt; ++j) {
+        int c = set_c0 + j * 32 + lane;
+        const bool in = c < p.Nin;
+        a[j] = in ? p.ccor[c] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    }
     int G = p.gt_counts[b];
     G = G < 0 ? 0 : (G > p.Gmax ? p.Gmax : G);
 
-    for (int tile = blockIdx.y; tile < p.tiles; tile += gridDim.y) {
-        const int c0 = tile * kTile;
-        const int set_c0 = c0 + set * kEncSet;
-        // flat anchor range whose outputs this tile writes: from its first inside anchor up to the next tile's
-        const int n_lo = (tile == 0) ? 0 : p.inside_idx[c0];
-        const int n_hi = (c0 + kTile >= p.Nin) ? p.N : p.inside_idx[c0 + kTile];
-
-        __syncthreads();                               // previous tile is done with shared memory
-        bool nice = true;
-        for (int g = tid; g < G; g += kEncThreads) {
-            float4 v = gtb[g];
-            s_box[g] = v;
-            s_area[g] = (v.w - v.y) * (v.z - v.x);
-            // start from the image-wide best published so far (any stale value is a valid lower
-            // bound): only overlaps that can still win reach the reduction path
-            s_best[g] = __ldcg(p.ws_keys + (size_t)b * p.Gmax + g);
-            nice = nice && nice_coord(v.x) && nice_coord(v.y) && nice_coord(v.z) && nice_coord(v.w);
-        }
-
-        // ---- this lane's anchors: corners + area in registers
-        float4 a[kEncApt];
-        float area[kEncApt];
-        float wy0 = CUDART_INF_F, wx0 = CUDART_INF_F, wy1 = -CUDART_INF_F, wx1 = -CUDART_INF_F;
-#pragma unroll
-        for (int j = 0; j < kEncApt; ++j) {
-            int c = set_c0 + j * 32 + lane;
-            const bool in = c < p.Nin;
-            a[j] = in ? p.ccor[c] : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-            area[j] = in ? (a[j].w - a[j].y) * (a[j].z - a[j].x) : 0.f;
-            wy0 = fminf(wy0, a[j].x);
-            wx0 = fminf(wx0, a[j].y);
-            wy1 = fmaxf(wy1, a[j].z);
-            wx1 = fmaxf(wx1, a[j].w);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            wy0 = fminf(wy0, __shfl_xor_sync(full, wy0, o));
-            wx0 = fminf(wx0, __shfl_xor_sync(full, wx0, o));
-            wy1 = fmaxf(wy1, __shfl_xor_sync(full, wy1, o));
-            wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
-        }
-        nice = __syncthreads_and(nice && p.anchors_nice) != 0;
-
-        float best[kEncApt];
-        int bestg[kEncApt];
-#pragma unroll
-        for (int j = 0; j < kEncApt; ++j) { best[j] = 0.f; bestg[j] = -1; }
-        const int per = (G + SPLIT - 1) / SPLIT;
-        const int g_lo = min(G, part * per), g_hi = min(G, g_lo + per);
-        if (nice)
-            sweep<true>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
-        else
-            sweep<false>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
-#pragma unroll
-        for (int j = 0; j < kEncApt; ++j) {
-            s_mv[part][set * kEncSet + j * 32 + lane] = best[j];
-            s_mg[part][set * kEncSet + j * 32 + lane] = bestg[j];
-        }
-        __syncthreads();
-
-        for (int g = tid; g < G; g += kEncThreads) {
-            u64 v = s_best[g];
-            // only keys this tile produced are above the value it started from
-            if (v != 0ull && v > __ldcg(p.ws_keys + (size_t)b * p.Gmax + g)) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
-        }
-
-        // ---- label + encode + store the tile's flat anchor range (forced anchors are rewritten
-        // by the CTA that finishes the image last)
-        for (int n = n_lo + tid; n < n_hi; n += kEncThreads) {
-            const int c = p.cidx[n];
-            float mv = 0.f;
-            int a2g = 0;
-            if (c >= 0) {
-                // parts hold ascending GT ranges: strict '>' keeps the lowest GT index on ties
-                int g = -1;
-#pragma unroll
-                for (int s = 0; s < SPLIT; ++s) {
-                    float v = s_mv[s][c - c0];
-                    if (v > mv) { mv = v; g = s_mg[s][c - c0]; }
-                }
-                a2g = g < 0 ? 0 : g;
-            }
-            bool less = mv < p.low;
-            bool between = (mv < p.high) && (mv >= p.low);
-            bool neg = p.ignore_between ? less : between;
-            bool ign = p.ignore_between ? between : less;
-            int mi = ign ? -2 : (neg ? -1 : a2g);
-            if (G == 0) mi = -1;
-            long long label = 0;
-            float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mi >= 0) {
-                label = p.gt_labels[(size_t)b * p.Gmax + a2g];
-                loc = encode_loc(s_box[a2g], p.enc[n], p);
-                if (!p.gt_max_first) atomicOr(p.ws_claimed + (size_t)b * p.Gmax + a2g, 1u);
-            } else if (mi < -1) {
-                label = -1;
-            }
-            size_t o = (size_t)b * p.N + n;
-            p.out_labels[o] = label;
-            p.out_loc[o] = loc;
-            p.out_scores[o] = mv;
-            if (p.out_matched) p.out_matched[o] = mi;
-            if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
-        }
-
-        // ---- publish; the last tile of the image applies the per-GT forcing.  Barrier first, then
-        // one thread fences and bumps the counter (release pattern of a grid-wide barrier).
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            unsigned prev = atomicAdd(p.ws_count + b, 1u);
-            s_last = (prev == (unsigned)p.tiles - 1u) ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            // s_best (8 B per GT slot) is free now: reuse it as two int arrays
-            force_image(p, b, G, reinterpret_cast<int*>(s_best), reinterpret_cast<int*>(s_best) + p.gcap);
-        }
+    bool nice = true;
+    for (int g = tid; g < G; g += kEncThreads) {
+        const float4 v = (g == tid) ? v_spec : gtb[g];
+        s_box[g] = v;
+        s_lab[g] = (g == tid) ? l_spec : gtl[g];
+        s_area[g] = (v.w - v.y) * (v.z - v.x);
+        // start from the image-wide best published so far (any stale value is a valid lower
+        // bound): only overlaps that can still win reach the reduction path
+        const u64 k0 = (g == tid) ? k_spec : __ldcg(wsk + g);
+        s_best[g] = k0;
+        s_init[g] = k0;
+        nice = nice && nice_coord(v.x) && nice_coord(v.y) && nice_coord(v.z) && nice_coord(v.w) &&
+               (v.z - v.x) <= 1.f && (v.w - v.y) <= 1.f;
     }
+#pragma unroll
+    for (int j = 0; j < kEncApt; ++j) {
+        const bool in = a[j].x != CUDART_INF_F;
+        area[j] = in ? (a[j].w - a[j].y) * (a[j].z - a[j].x) : 0.f;
+        wy0 = fminf(wy0, a[j].x);
+        wx0 = fminf(wx0, a[j].y);
+        wy1 = fmaxf(wy1, a[j].z);
+        wx1 = fmaxf(wx1, a[j].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wy0 = fminf(wy0, __shfl_xor_sync(full, wy0, o));
+        wx0 = fminf(wx0, __shfl_xor_sync(full, wx0, o));
+        wy1 = fmaxf(wy1, __shfl_xor_sync(full, wy1, o));
+        wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
+    }
+    nice = __syncthreads_and(nice && p.anchors_nice) != 0;
+
+    float best[kEncApt];
+    int bestg[kEncApt];
+#pragma unroll
+    for (int j = 0; j < kEncApt; ++j) { best[j] = 0.f; bestg[j] = -1; }
+    const int per = (G + SPLIT - 1) / SPLIT;
+    const int g_lo = min(G, part * per), g_hi = min(G, g_lo + per);
+    if (nice)
+        sweep<true>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
+    else
+        sweep<false>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
+#pragma unroll
+    for (int j = 0; j < kEncApt; ++j) {
+        s_mv[part][set * kEncSet + j * 32 + lane] = best[j];
+        s_mg[part][set * kEncSet + j * 32 + lane] = bestg[j];
+    }
+    __syncthreads();
+
+    for (int g = tid; g < G; g += kEncThreads) {
+        u64 v = s_best[g];
+        // only keys this tile produced are above the value it started from
+        if (v > s_init[g]) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
+    }
+
+    // ---- label + encode + store the item's flat anchor range (forced anchors are rewritten
+    // by the CTA that finishes the image last)
+    int q = 0;
+    for (int n = n_lo + tid; n < n_hi; n += kEncThreads, ++q) {
+        int c;
+        switch (q) {                                       // compile-time register selection
+            case 0: c = cpre[0]; break;
+            case 1: c = cpre[1]; break;
+            case 2: c = cpre[2]; break;
+            case 3: c = cpre[3]; break;
+            default: c = p.cidx[n]; break;
+        }
+        float mv = 0.f;
+        int a2g = 0;
+        if (c >= 0) {
+            // parts hold ascending GT ranges: strict '>' keeps the lowest GT index on ties
+            int g = -1;
+#pragma unroll
+            for (int s = 0; s < SPLIT; ++s) {
+                float v = s_mv[s][c - c0];
+                if (v > mv) { mv = v; g = s_mg[s][c - c0]; }
+            }
+            a2g = g < 0 ? 0 : g;
+        }
+        bool less = mv < p.low;
+        bool between = (mv < p.high) && (mv >= p.low);
+        bool neg = p.ignore_between ? less : between;
+        bool ign = p.ignore_between ? between : less;
+        int mi = ign ? -2 : (neg ? -1 : a2g);
+        if (G == 0) mi = -1;
+        long long label = 0;
+        float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mi >= 0) {
+            label = s_lab[a2g];
+            loc = encode_loc(s_box[a2g], p.enc[n], p);
+            if (!p.gt_max_first) atomicOr(p.ws_claimed + (size_t)b * p.Gmax + a2g, 1u);
+        } else if (mi < -1) {
+            label = -1;
+        }
+        size_t o = (size_t)b * p.N + n;
+        p.out_labels[o] = label;
+        p.out_loc[o] = loc;
+        p.out_scores[o] = mv;
+        if (p.out_matched) p.out_matched[o] = mi;
+        if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
+    }
+
+    // ---- publish; the last item of the image applies the per-GT forcing.  Barrier first, then
+    // one thread fences and bumps the counter (release pattern of a grid-wide barrier).
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned prev = atomicAdd(p.ws_count + b, 1u);
+        s_last = (prev == (unsigned)p.tiles - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        // s_best (8 B per GT slot) is free now: reuse it as two int arrays
+        force_image<kEncThreads>(p, b, G, reinterpret_cast<int*>(s_best), reinterpret_cast<int*>(s_best) + p.gcap);
+    }
+}
+
+// grid (B, items): blockIdx.y walks the handle's work-item table (heavy, coarse-layer items first)
+__global__ void __launch_bounds__(kEncThreads, 10)
+match_encode_kernel(const __grid_constant__ EncodeParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int4 item = __ldg(p.items + blockIdx.y);
+    if (item.w == 4)
+        encode_item<1, 4>(p, smem, blockIdx.x, item.x, item.y, item.z);
+    else
+        encode_item<4, 1>(p, smem, blockIdx.x, item.x, item.y, item.z);
 }
 
 __global__ void zero_u32_kernel(unsigned* p, size_t n) {
@@ -413,27 +460,22 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     p.ws_count = p.ws_claimed + (size_t)B * Gmax;
 
     p.anchors_nice = h->anchors_nice;
-    // Small batches cannot fill 148 SMs x 32 warps with whole-GT-list items: split the GT list of
-    // every 64-anchor set over the CTA's four warps instead (4x more, 4x shorter items).
-    const int sets_total = (p.Nin + kEncSet - 1) / kEncSet;
-    const long long items = (long long)B * sets_total, slots = (long long)h->num_sms * 32;
-    int split = items < slots * 2 ? 4 : (items < slots * 6 ? 2 : 1);
-    if (const char* e = getenv("RONK_ENC_SPLIT")) {          // tuning knob (1, 2 or 4)
+    // Work-item table: the batch decides how finely the heaviest items are cut.  A tiny batch cannot
+    // fill 148 SMs x 40 warps with whole-GT-list items, and the kernel then lasts as long as its
+    // slowest CTA (a coarse-layer tile against 50 GT boxes): cut those (table 1) or everything
+    // (table 2) into 4 GT parts.  Large batches keep whole items (table 0): least overhead.
+    const long long sets = (long long)B * ((p.Nin + kEncSet - 1) / kEncSet), slots = (long long)h->num_sms * 40;
+    int table = sets < slots / 2 ? 2 : (sets < slots * 2 ? 1 : 0);   // measured crossovers: batch ~13 and ~55 for RON-320
+    if (const char* e = getenv("RONK_ENC_TABLE")) {            // tuning knob
         int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4) split = v;
+        if (v >= 0 && v <= 2) table = v;
     }
-    const int tile_anchors = (kEncWarps / split) * kEncSet;
-    p.tiles = (p.Nin + tile_anchors - 1) / tile_anchors;
-    if (p.tiles < 1) p.tiles = 1;
-    size_t smem = (size_t)p.gcap * (16 + 8 + 4);
+    p.items = (const int4*)h->d_items[table];
+    p.tiles = h->n_items[table];
+    RONK_REQUIRE(p.tiles <= 65535, RONK_ELIMIT, "ronk_match_encode: too many anchors for one launch");
+    size_t smem = (size_t)p.gcap * (16 + 8 + 8 + 8 + 4);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)B, (unsigned)(p.tiles < 65535 ? p.tiles : 65535));
-    if (split == 4)
-        match_encode_kernel<1, 4><<<grid, kEncThreads, smem, st>>>(p);
-    else if (split == 2)
-        match_encode_kernel<2, 2><<<grid, kEncThreads, smem, st>>>(p);
-    else
-        match_encode_kernel<4, 1><<<grid, kEncThreads, smem, st>>>(p);
+    match_encode_kernel<<<dim3((unsigned)B, (unsigned)p.tiles), kEncThreads, smem, st>>>(p);
     RONK_LAUNCHED();
     return RONK_OK;
 }

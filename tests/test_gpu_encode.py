@@ -183,8 +183,10 @@ def test_encode_extreme_coordinates(ron, batch):
     boxes, labels, counts = synth.make_gt_batch(7, batch, 3, 12)
     boxes = boxes.copy()
     for b in range(batch):
-        k = b % 4
-        if k == 0:
+        k = b % 5
+        if k == 4:
+            boxes[b, 0] = [-0.3, -0.2, 1.4, 1.3]                 # sides > 1: the saturating clamp must not be used
+        elif k == 0:
             boxes[b, 0] = [1e-7, 3e-6, 0.4, 0.5]                 # tiny non-zero corner
         elif k == 1:
             boxes[b, 1] = [0.25, 0.25, 0.25 + 1e-6, 0.75]        # sliver
