@@ -28,10 +28,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENC_B, ENC_G = 64, (1, 50)
+WORKLOAD = ('BASELINE configs[1]: RON-320 joint match+encode over all 4 layers (21250 anchors), batch 64 per GPU, '
+            '1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels')
 POST_B, POST_K, POST_M, POST_THR = 256, 400, 200, 0.45
 N_ANCHORS, N_CLASSES = 21250, 21
 ENC_BYTES_PER_IMAGE = N_ANCHORS * 28          # labels i64 + loc 4xf32 + score f32; + 24 B per GT
 POST_BYTES_PER_IMAGE = N_ANCHORS * (4 * N_CLASSES + 16 + 4) + (N_CLASSES - 1) * POST_M * 20
+
+
+def traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    try:
+        v = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json'))).get(key)
+        return sum(v.values()) if isinstance(v, dict) else v
+    except Exception:
+        return None
 
 
 def peaks():
@@ -163,8 +174,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'images/sec (match+encode)', 'value': v_enc, 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1]: RON-320 joint match+encode, 1-50 GT/image, thresholds 0.56/0.3 '
-                               '(CPU: NumPy restatement of the reference TF-1 graph, %d images per step)' % n_enc},
+        'config': {'workload': WORKLOAD, 'l2': 'n/a (host)',
+                   'cpu': 'NumPy restatement of the reference TF-1 graph (TensorFlow 1.x is not installable), '
+                          '%d images per step over %d worker processes' % (n_enc, cores)},
         'cpu_baseline': {'value': v_enc, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                          'sample': '%d images per step x %d steps, %d worker processes' % (n_enc, args.steps, cores)},
         'e2e': {'value': v_enc, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -278,7 +290,8 @@ def run_ours(args):
               'ms_per_step': float(np.mean(ms256)),
               'config': {'workload': 'same path, batch 256 per GPU', 'l2': 'outputs (152 MB/step, 4 rotating sets) exceed L2'},
               'roofline': {'bound': 'hbm', 'achieved': enc256_bytes / (np.mean(ms256) * 1e-3) / 1e9, 'peak': hbm,
-                           'unit': 'GB/s', 'frac': enc256_bytes / (np.mean(ms256) * 1e-3) / 1e9 / hbm, 'traffic': None}}
+                           'unit': 'GB/s', 'frac': enc256_bytes / (np.mean(ms256) * 1e-3) / 1e9 / hbm,
+                           'traffic': traffic('match_encode_b256')}}
     del outs2
 
     # e2e: pinned host GT -> device, kernels, targets back to pinned host memory, every step
@@ -371,8 +384,9 @@ def run_ours(args):
                                    'select 0.01, clip, min-size 0.03, top-k %d, NMS min-area %.2f keep %d, + VOC TP/FP kernel'
                                    % (POST_B, POST_K, POST_THR, POST_M), 'l2': 'inputs (586 MB) exceed L2'},
             'roofline': {'bound': 'hbm', 'achieved': post_achieved, 'peak': hbm, 'unit': 'GB/s',
-                         'frac': post_achieved / hbm, 'traffic': None, 'peak_source': peak_src,
-                         'note': 'algorithmic 2.29 MB/image over the whole step (3 select + 1 NMS + 1 TP/FP launches)'},
+                         'frac': post_achieved / hbm, 'traffic': traffic('postprocess_b256'), 'peak_source': peak_src,
+                         'note': 'algorithmic 2.29 MB/image over the whole step (init, scatter x2, pivot, top-k, NMS, TP/FP: '
+                                 '7 launches); traffic is the ncu DRAM total of the scatter/top-k/TP-FP launches'},
             'e2e': {'value': post_e2e, 'unit': 'images/s',
                     'h2d_bytes_per_step': int(sum(t.numel() * 4 for t in h_loc + h_pred + h_obj)),
                     'd2h_bytes_per_step': int(h_s.numel() * 4 + h_b.numel() * 4)},
@@ -399,13 +413,12 @@ def run_ours(args):
             'metric': 'images/sec (match+encode)', 'value': enc_value, 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(ms)), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[1]: RON-320 joint match+encode over all 4 layers (21250 anchors), '
-                                   'batch %d per GPU, 1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels'
-                                   % ENC_B, 'l2': 'flushed between timed steps (256 MB write)'},
+            'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)'},
             'roofline': {'bound': 'hbm', 'achieved': enc_achieved, 'peak': hbm, 'unit': 'GB/s',
-                         'frac': enc_achieved / hbm, 'traffic': None, 'peak_source': peak_src,
-                         'note': 'algorithmic %d B/batch over the whole step (match_encode_kernel + match_force_kernel)'
-                                 % enc_bytes},
+                         'frac': enc_achieved / hbm, 'traffic': traffic('match_encode_b64'), 'peak_source': peak_src,
+                         'note': 'algorithmic %d B/batch, one match_encode_kernel launch per step; the kernel is FP32-issue '
+                                 'bound (DESIGN.md 4.2); ncu DRAM traffic is far below the algorithmic bytes because the 38 MB '
+                                 'of outputs are still in the 126 MB L2 when the kernel ends' % enc_bytes},
             'cpu_baseline': cpu,
             'e2e': {'value': enc_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': int(enc_h2d),
                     'd2h_bytes_per_step': int(enc_d2h)},

@@ -371,7 +371,7 @@ def tpfp_match(det_scores, det_boxes, glabels, gboxes, gdifficults, matching_thr
         rc = _ffi.lib().ronk_tpfp_match(_ptr(s), _ptr(b), B, CM + 1, M, _ptr(gl), _ptr(gb), _ptr(gd), G,
                                         float(matching_threshold), _ptr(n_gt), _ptr(tp), _ptr(fp), _stream())
     _ffi.check(rc)
-    return n_gt, tp.bool(), fp.bool()
+    return n_gt, tp.view(torch.bool), fp.view(torch.bool)      # 0/1 bytes: a view, no conversion kernel
 
 
 def launch_count():

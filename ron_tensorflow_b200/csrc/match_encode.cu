@@ -177,7 +177,8 @@ __device__ __forceinline__ void sweep(const float4* s_box, const float* s_area, 
             for (int q = 0; q < 2; ++q) {
                 t[q] = s_box[gq[q]];
                 ga[q] = s_area[gq[q]];
-                // stale values are only lower: a safe filter; >= 1 so that zero overlaps never pass
+                // s_best is this warp's private copy (seeded with the image-wide best when the item
+                // started); >= 1 so that zero overlaps never pass
                 cur[q] = max((unsigned)(s_best[gq[q]] >> 32), 1u);
             }
             unsigned bits[2][kEncApt];
@@ -207,8 +208,9 @@ __device__ __forceinline__ void sweep(const float4* s_box, const float* s_area, 
                     const unsigned first = __reduce_min_sync(full, cand);
                     if (lane == 0) {
                         u64 key = ((u64)m << 32) | (u64)(0xffffffffu - (set_c0 + first));
-                        atomicMax(&s_best[gq[q]], key);
+                        if (key > s_best[gq[q]]) s_best[gq[q]] = key;       // private to this warp: no atomic
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -226,8 +228,8 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
     static_assert(SETS * SPLIT * 32 == kEncThreads, "4 warps per CTA");
     constexpr int kTile = SETS * kEncSet;
     float4* s_box = reinterpret_cast<float4*>(smem);              // [gcap] GT corners
-    u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [gcap] per-GT (iou bits, ~compact anchor) of this tile
-    u64* s_init = s_best + p.gcap;                                // [gcap] image-wide best when this tile started
+    u64* s_best = reinterpret_cast<u64*>(s_box + p.gcap);         // [4][gcap] per warp: per-GT (iou bits, ~compact anchor)
+    u64* s_init = s_best + 4 * p.gcap;                            // [gcap] image-wide best when this item started
     long long* s_lab = reinterpret_cast<long long*>(s_init + p.gcap);   // [gcap] GT labels
     float* s_area = reinterpret_cast<float*>(s_lab + p.gcap);     // [gcap]
     __shared__ float s_mv[SPLIT][kTile];                          // per-anchor max overlap, per GT part
@@ -276,7 +278,8 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
         // start from the image-wide best published so far (any stale value is a valid lower
         // bound): only overlaps that can still win reach the reduction path
         const u64 k0 = (g == tid) ? k_spec : __ldcg(wsk + g);
-        s_best[g] = k0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s_best[w * p.gcap + g] = k0;
         s_init[g] = k0;
         nice = nice && nice_coord(v.x) && nice_coord(v.y) && nice_coord(v.z) && nice_coord(v.w) &&
                (v.z - v.x) <= 1.f && (v.w - v.y) <= 1.f;
@@ -306,9 +309,9 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
     const int per = (G + SPLIT - 1) / SPLIT;
     const int g_lo = min(G, part * per), g_hi = min(G, g_lo + per);
     if (nice)
-        sweep<true>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
+        sweep<true>(s_box, s_area, s_best + warp * p.gcap, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
     else
-        sweep<false>(s_box, s_area, s_best, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
+        sweep<false>(s_box, s_area, s_best + warp * p.gcap, g_lo, g_hi, a, area, wy0, wx0, wy1, wx1, (unsigned)set_c0, best, bestg);
 #pragma unroll
     for (int j = 0; j < kEncApt; ++j) {
         s_mv[part][set * kEncSet + j * 32 + lane] = best[j];
@@ -318,7 +321,9 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
 
     for (int g = tid; g < G; g += kEncThreads) {
         u64 v = s_best[g];
-        // only keys this tile produced are above the value it started from
+#pragma unroll
+        for (int w = 1; w < 4; ++w) v = max(v, s_best[w * p.gcap + g]);
+        // only keys this item produced are above the value it started from
         if (v > s_init[g]) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
     }
 
@@ -473,8 +478,10 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     p.items = (const int4*)h->d_items[table];
     p.tiles = h->n_items[table];
     RONK_REQUIRE(p.tiles <= 65535, RONK_ELIMIT, "ronk_match_encode: too many anchors for one launch");
-    size_t smem = (size_t)p.gcap * (16 + 8 + 8 + 8 + 4);
+    size_t smem = (size_t)p.gcap * (16 + 4 * 8 + 8 + 8 + 4);
     cudaStream_t st = (cudaStream_t)stream;
+    if (smem > 48 * 1024)
+        RONK_CUDA(cudaFuncSetAttribute(match_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     match_encode_kernel<<<dim3((unsigned)B, (unsigned)p.tiles), kEncThreads, smem, st>>>(p);
     RONK_LAUNCHED();
     return RONK_OK;

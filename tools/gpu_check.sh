@@ -33,5 +33,5 @@ for k, v in sorted(t.items(), key=lambda kv: -sum(kv[1])):
 PY
 if [ "$2" = "full" ]; then
   ncu --set full --clock-control none --import-source on -k regex:match_encode -s 2 -c 1 -o gpurun_out/${tag}_enc python tools/prof.py --stage encode --batch 256 --iters 3 > /dev/null 2>&1
-  ncu --set full --clock-control none --import-source on -k 'regex:scatter|select_topk|nms_kernel|tpfp' -s 4 -c 4 -o gpurun_out/${tag}_post python tools/prof.py --stage post --batch 256 --iters 2 > /dev/null 2>&1
+  ncu --set full --clock-control none --import-source on -k 'regex:scatter|pivot|select_topk|nms_kernel|tpfp' -s 6 -c 6 -o gpurun_out/${tag}_post python tools/prof.py --stage post --batch 256 --iters 2 > /dev/null 2>&1
 fi

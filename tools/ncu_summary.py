@@ -21,7 +21,7 @@ WANT = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
 w = csv.writer(sys.stdout)
 first = True
 for rep in sys.argv[1:]:
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv', '--print-units', 'base'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     if len(rows) < 3:
         continue
