@@ -23,6 +23,7 @@ import time
 
 import numpy as np
 
+print_line = print
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -184,7 +185,7 @@ def run_reference(args):
         'stages': {'postprocess': {'value': v_post, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                    'sample': '%d images, decode+gate+top-400+NMS(0.45,keep 200)' % n_post}},
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -196,7 +197,9 @@ def timed_steps(torch, fn, steps, warmup, flush=None):
         if flush is not None:
             flush.zero_()
     torch.cuda.synchronize()
+    from ron_tensorflow_b200 import core
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    l0 = core.launch_count()
     for a, b in evs:
         if flush is not None:
             flush.zero_()
@@ -204,6 +207,7 @@ def timed_steps(torch, fn, steps, warmup, flush=None):
         fn()
         b.record()
     torch.cuda.synchronize()
+    timed_steps.launches = core.launch_count() - l0       # libronk kernels launched inside the timed steps
     return [a.elapsed_time(b) for a, b in evs]      # ms
 
 
@@ -260,9 +264,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    l0 = core.launch_count()
     ms = timed_steps(torch, enc_step, args.steps, args.warmup, flush)
-    enc_launches = core.launch_count() - l0
+    enc_launches = timed_steps.launches
     barrier()
     t_enc = max_over_ranks(sum(ms) / 1e3)
     enc_value = ENC_B * args.steps * world / t_enc
@@ -338,9 +341,8 @@ def run_ours(args):
             res['tpfp'] = core.tpfp_match(ns, nb, d_gl, d_gb, d_gd, 0.5)
 
         barrier()
-        l1 = core.launch_count()
         ms_p = timed_steps(torch, post_step, args.steps, args.warmup)       # inputs (586 MB) exceed L2
-        post_launches = core.launch_count() - l1
+        post_launches = timed_steps.launches
         barrier()
         t_post = max_over_ranks(sum(ms_p) / 1e3)
         post_value = POST_B * args.steps * world / t_post
@@ -426,7 +428,7 @@ def run_ours(args):
             'clocks': clocks,
             'stages': {'encode_b256': enc256, 'postprocess': post},
         }
-        print(json.dumps(line))
+        print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -442,6 +444,14 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version banner)
+    # is sent to stderr instead
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, 'w')
+    global print_line
+    print_line = lambda line: (out.write(line + '\n'), out.flush())
     if args.impl == 'reference':
         run_reference(args)
     else:

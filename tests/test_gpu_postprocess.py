@@ -265,3 +265,82 @@ def test_topk_paths_vs_oracle(ron, dec_anchors, path, dense, K):
         eq(ix[b], oi, 'anchor idx b=%d' % b)
         eq(s[b], os_, 'scores b=%d' % b)
         eq(bx[b], ob, 'boxes b=%d' % b)
+
+
+def test_ssd512_postprocess_vs_oracle():
+    """BASELINE config 4 shape on the post-process side: SSD-512 anchors (24 564, 7 layers, tiles
+    that end mid-row), SSD order (no objectness gate, no clip, no min-size)."""
+    need_cuda()
+    from ron_tensorflow_b200.nets import ssd_vgg_512
+    net = ssd_vgg_512.SSDNet()
+    anchors = net.anchors(net.params.img_shape)
+    ls = anchors.anchor_set.layer_sizes
+    assert sum(ls) == 24564
+    B = 2
+    loc, pred, _ = synth.make_predictions(512, B, 24564, 21, hot=200)
+    dec = O.flat_decode_anchors(O.anchors_all_layers(O.SSD512))
+    ns, nb = net.detect(synth.split_layers(pred, ls), synth.split_layers(loc, ls), select_threshold=0.02,
+                        nms_threshold=0.45, top_k=400, keep_top_k=200)
+    for b in range(B):
+        o = O.detected_bboxes_image(pred[b], loc[b], dec, None, None, 0.02, 0.45, None, 400, 200, min_size=None)
+        eq(ns[b], o['scores'], 'scores b=%d' % b)
+        eq(nb[b], o['boxes'], 'boxes b=%d' % b)
+
+
+def test_crowded_81_classes_topk_10000(ron, dec_anchors):
+    """BASELINE config 5 shape: 81 classes, dense scores (~10k candidates per class), K = 10 000
+    (beyond the register/shared-memory paths of the top-k kernel) and K = 400."""
+    from ron_tensorflow_b200 import core
+    net, anchors = ron
+    loc, pred, obj = synth.make_predictions(5005, 1, 21250, 81, hot=2000, dense=True)
+    obj = np.maximum(obj, np.float32(0.05))                      # every anchor passes the objectness gate
+    boxes = O.decode(loc[0], dec_anchors)
+    for K in (10000, 400):
+        s, bx, ix = core.decode_select_topk(anchors.anchor_set, _layers(loc, False), _layers(pred, False),
+                                            _layers(obj, False), 0.03, 0.004, [0., 0., 1., 1.], 0.03, K, want_idx=True)
+        os_, ob, oi = O.select_topk_image(pred[0], boxes, 0.004, K, [0., 0., 1., 1.], 0.03)
+        assert int((os_ > 0).sum(1).max()) > 5000 or K == 400
+        eq(ix[0], oi, 'anchor idx K=%d' % K)
+        eq(s[0], os_, 'scores K=%d' % K)
+        eq(bx[0], ob, 'boxes K=%d' % K)
+
+
+def test_property_full_size_postprocess_batch256(ron, dec_anchors):
+    """BASELINE config 3 at full size (batch 256): size-independent properties of the whole chain
+    plus the oracle on a sample of the images.  Properties: scores sorted per (image, class); zero
+    padding only at the tail; every kept pair respects the NMS threshold (min-area overlap < 0.45);
+    running NMS again on the output keeps everything (idempotence); TP/FP flags are disjoint and
+    TP count <= GT count."""
+    import torch
+    from ron_tensorflow_b200 import core
+    net, anchors = ron
+    B = 256
+    loc, pred, obj = synth.make_predictions(3000, B, 21250, 21, hot=300)
+    ns, nb, ni = net.detect(_layers(pred, False), _layers(loc, False), _layers(obj, False), 0.03, 0.01, 0.45,
+                            [0., 0., 1., 1.], 400, 200, want_idx=True)
+    assert ns.shape == (B, 20, 200)
+    assert bool((ns[..., :-1] >= ns[..., 1:]).all()), 'scores must be sorted'
+    real = ns > 0
+    assert bool((real[..., :-1] | ~real[..., 1:]).all()), 'padding only at the tail'
+    assert bool(((ni >= 0) == real).all())
+    # pairwise min-area overlap among the kept boxes of a few (image, class) rows
+    for b, c in [(0, 0), (17, 5), (255, 19), (128, 11)]:
+        k = int(real[b, c].sum())
+        bx = nb[b, c, :k].double()
+        ih = (torch.minimum(bx[:, None, 2], bx[None, :, 2]) - torch.maximum(bx[:, None, 0], bx[None, :, 0])).clamp(min=0)
+        iw = (torch.minimum(bx[:, None, 3], bx[None, :, 3]) - torch.maximum(bx[:, None, 1], bx[None, :, 1])).clamp(min=0)
+        area = (bx[:, 2] - bx[:, 0]) * (bx[:, 3] - bx[:, 1])
+        ov = ih * iw / torch.minimum(area[:, None], area[None, :])
+        ov.fill_diagonal_(0)
+        assert float(ov.max()) < 0.45 + 1e-6
+    ns2, nb2, _ = core.nms_batch(ns.view(-1, 200), nb.view(-1, 200, 4), 0.45, 200, 'min', assume_sorted=True)
+    assert torch.equal(ns2.view_as(ns), ns) and torch.equal(nb2.view_as(nb), nb), 'NMS must be idempotent'
+    gb, gl, gc = synth.make_gt_batch(3, B, 1, 12, g_max=12)
+    n_gt, tp, fp = core.tpfp_match(ns, nb, gl, gb, gl * 0, 0.5)
+    assert not bool((tp & fp).any())
+    assert bool((tp.sum(-1) <= n_gt).all())
+    for b in (0, 101, 255):
+        o = O.detected_bboxes_image(pred[b], loc[b], dec_anchors, obj[b], 0.03, 0.01, 0.45, [0., 0., 1., 1.], 400, 200)
+        eq(ni[b], o['idx'], 'kept anchor indices b=%d' % b)
+        eq(ns[b], o['scores'], 'scores b=%d' % b)
+        eq(nb[b], o['boxes'], 'boxes b=%d' % b)
