@@ -58,12 +58,15 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.x * kNmsWarps + warp;
     if (seg >= p.S) return;
-    const int per_warp = ((p.M + 32) * 20 + 15) & ~15;   // float4 + float for M kept and 32 chunk entries
+    const int per_warp = ((p.M + 32) * 20 + p.M * 4 + 15) & ~15;   // float4 + float for M kept and 32 chunk entries, + thr * vol
     unsigned char* base = smem + (size_t)warp * per_warp;
     float4* s_kbox = reinterpret_cast<float4*>(base);
     float4* s_cbox = s_kbox + p.M;
     float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
     float* s_cvol = s_kvol + p.M;
+    float* s_kt = s_cvol + 32;            // thr * vol of the kept boxes (+inf for empty boxes: they suppress nothing)
+    // fast 'min' loop: valid while thr > 0 and every box seen so far has all corners in [0, 1]
+    bool unit = (p.mode == RONK_NMS_MIN) && (p.thr > 0.f);
 
     const bool zero_supp = !(0.f < p.thr);
     const size_t in0 = (size_t)seg * p.K, out0 = (size_t)seg * p.M;
@@ -85,23 +88,48 @@ nms_kernel(const __grid_constant__ NmsParams p) {
         //    NaNs, the chunk is redone with the exact division below).
         bool dead = !valid;
         bool unclear = false;
-        for (int i0 = 0; i0 < count; i0 += 8) {
-            const int lim = min(8, count - i0);
+        unit = unit && __all_sync(full, box.x >= 0.f && box.y >= 0.f && box.z <= 1.f && box.w <= 1.f &&
+                                            box.x <= 1.f && box.y <= 1.f && box.z >= 0.f && box.w >= 0.f);
+        if (unit) {
+            // overlap = inner / min(vol_j, vol_i) >= thr  <=>  inner >= min(thr vol_j, thr vol_i) (rounding is
+            // monotonic).  Sides are <= 1, so max(., 0) is a saturating subtract (FMA pipe); the band in
+            // which the exact division must decide is taken against thr vol_j >= min(.): conservative.
+            const float tj = p.thr * vol;
+            const float tolj = tj * 1e-6f;
+            for (int i0 = 0; i0 < count; i0 += 8) {
+                const int lim = min(8, count - i0);
 #pragma unroll 4
-            for (int i = 0; i < lim; ++i) {
-                const float4 kb = s_kbox[i0 + i];
-                const float kv = s_kvol[i0 + i];
-                const float h = fmaxf(fminf(box.z, kb.z) - fmaxf(box.x, kb.x), 0.f);
-                const float w = fmaxf(fminf(box.w, kb.w) - fmaxf(box.y, kb.y), 0.f);
-                const float inner = h * w;
-                const float den = (p.mode == RONK_NMS_UNION) ? ((vol - inner) + kv) : fminf(vol, kv);
-                const float t = p.thr * den;
-                const float d = inner - t;
-                const bool pos = den > 0.f;                       // else safe_divide gives overlap 0
-                dead |= pos ? (d > 0.f) : zero_supp;
-                unclear |= pos && !(fabsf(d) > t * 1e-6f);
+                for (int i = 0; i < lim; ++i) {
+                    const float4 kb = s_kbox[i0 + i];
+                    const float kt = s_kt[i0 + i];
+                    const float h = __saturatef(fminf(box.z, kb.z) - fmaxf(box.x, kb.x));
+                    const float w = __saturatef(fminf(box.w, kb.w) - fmaxf(box.y, kb.y));
+                    const float d = h * w - fminf(tj, kt);
+                    dead |= d > 0.f;
+                    unclear |= fabsf(d) <= tolj;
+                }
+                if (__all_sync(full, dead)) break;
             }
-            if (__all_sync(full, dead)) break;
+            if (valid && !(vol > 0.f)) { dead = false; unclear = false; }     // empty candidate: overlap is 0 everywhere
+        } else {
+            for (int i0 = 0; i0 < count; i0 += 8) {
+                const int lim = min(8, count - i0);
+#pragma unroll 4
+                for (int i = 0; i < lim; ++i) {
+                    const float4 kb = s_kbox[i0 + i];
+                    const float kv = s_kvol[i0 + i];
+                    const float h = fmaxf(fminf(box.z, kb.z) - fmaxf(box.x, kb.x), 0.f);
+                    const float w = fmaxf(fminf(box.w, kb.w) - fmaxf(box.y, kb.y), 0.f);
+                    const float inner = h * w;
+                    const float den = (p.mode == RONK_NMS_UNION) ? ((vol - inner) + kv) : fminf(vol, kv);
+                    const float t = p.thr * den;
+                    const float d = inner - t;
+                    const bool pos = den > 0.f;                       // else safe_divide gives overlap 0
+                    dead |= pos ? (d > 0.f) : zero_supp;
+                    unclear |= pos && !(fabsf(d) > t * 1e-6f);
+                }
+                if (__all_sync(full, dead)) break;
+            }
         }
         if (__any_sync(full, unclear && valid)) {
             dead = !valid;
@@ -129,6 +157,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
             int r = count + __popc(kept & ((1u << lane) - 1u));
             s_kbox[r] = box;
             s_kvol[r] = vol;
+            s_kt[r] = (vol > 0.f) ? p.thr * vol : __int_as_float(0x7f800000);
             p.out_scores[out0 + r] = score;
             p.out_boxes[out0 + r] = box;
             if (p.out_idx) p.out_idx[out0 + r] = pos;
@@ -205,7 +234,7 @@ extern "C" int ronk_nms_batch(const float* scores, const float* boxes, int S, in
         RONK_LAUNCHED();
         p.order = (const int*)ws;
     }
-    size_t smem = (size_t)kNmsWarps * ((((size_t)keep_top_k + 32) * 20 + 15) & ~(size_t)15);
+    size_t smem = (size_t)kNmsWarps * ((((size_t)keep_top_k + 32) * 20 + (size_t)keep_top_k * 4 + 15) & ~(size_t)15);
     if (smem > 48 * 1024)
         RONK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_kernel<<<(S + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, smem, st>>>(p);

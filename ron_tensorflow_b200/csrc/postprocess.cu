@@ -401,36 +401,32 @@ __device__ __forceinline__ void block_bitonic_desc(u64* s_sort, int P) {
     }
 }
 
-// The same network for P = 256 * EPT with the elements in registers (thread t owns elements
-// EPT*t .. EPT*t+EPT-1): strides below EPT stay inside the thread, strides below 32*EPT are warp
-// shuffles, only the log2(256/32) coarsest strides of each merge go through shared memory.
+// Sort of s_sort[0..P), P = 256 * EPT, descending, distinct keys (zeros allowed, they end up last):
+//  A. every warp sorts its run of 32 * EPT consecutive elements in registers (bitonic network, warp
+//     shuffles, no barrier);
+//  B. log2(8) merge levels: each element finds its rank in the sibling run with a branch-free binary
+//     search (one dependent shared-memory read per step) and is written to its final position of the
+//     merged run in the other buffer.  3 barriers per level instead of a barrier per bitonic stage,
+//     and ~1/3 of the instructions.
+// s_tmp: P u64 of scratch.  The result is back in s_sort.
 template <int EPT>
-__device__ __forceinline__ void block_bitonic_regs(u64* s_sort) {
+__device__ __forceinline__ void block_sort_desc(u64* s_sort, u64* s_tmp) {
     constexpr int P = kTopkThreads * EPT;
+    constexpr int L0 = 32 * EPT;
     const int tid = threadIdx.x;
     const unsigned full = 0xffffffffu;
     u64 v[EPT];
 #pragma unroll
     for (int r = 0; r < EPT; ++r) v[r] = s_sort[EPT * tid + r];
-    for (int size = 2; size <= P; size <<= 1) {
+#pragma unroll
+    for (int size = 2; size <= L0; size <<= 1) {
+#pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32 * EPT) {
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < EPT; ++r) s_sort[EPT * tid + r] = v[r];
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < EPT; ++r) {
-                    const int e = EPT * tid + r;
-                    const u64 o = s_sort[e ^ stride];
-                    const bool keep_max = (((e & stride) == 0) == ((e & size) == 0));
-                    v[r] = (keep_max == (o > v[r])) ? o : v[r];
-                }
-            } else if (stride >= EPT) {
+            if (stride >= EPT) {
                 const int lm = stride / EPT;
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
-                    const int e = EPT * tid + r;
+                    const int e = (EPT * tid + r) & (L0 - 1);              // position inside the run
                     const u64 o = __shfl_xor_sync(full, v[r], lm);
                     const bool keep_max = (((e & stride) == 0) == ((e & size) == 0));
                     v[r] = (keep_max == (o > v[r])) ? o : v[r];
@@ -439,7 +435,7 @@ __device__ __forceinline__ void block_bitonic_regs(u64* s_sort) {
 #pragma unroll
                 for (int r = 0; r < EPT; ++r) {
                     if ((r & stride) == 0) {
-                        const int e = EPT * tid + r;
+                        const int e = (EPT * tid + r) & (L0 - 1);
                         const bool desc = ((e & size) == 0);
                         const u64 x = v[r], y = v[r | stride];
                         if ((x < y) == desc) { v[r] = y; v[r | stride] = x; }
@@ -448,10 +444,43 @@ __device__ __forceinline__ void block_bitonic_regs(u64* s_sort) {
             }
         }
     }
+    u64* src = s_sort;
+    u64* dst = s_tmp;
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < EPT; ++r) s_sort[EPT * tid + r] = v[r];
+    for (int r = 0; r < EPT; ++r) src[EPT * tid + r] = v[r];
     __syncthreads();
+#pragma unroll
+    for (int L = L0; L < P; L <<= 1) {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+            const int e = EPT * tid + r;
+            const u64 x = src[e];
+            const int run = e / L, i = e & (L - 1);
+            const u64* sib = src + (run ^ 1) * L;
+            const bool odd = run & 1;
+            // number of sibling elements that precede x in the merged (descending) order:
+            // y > x, and y == x too when the sibling is the left run (only zeros can be equal)
+            int pos = 0;
+#pragma unroll
+            for (int st = L >> 1; st > 0; st >>= 1) {
+                const u64 y = sib[pos + st - 1];
+                if (y > x || (odd && y == x)) pos += st;
+            }
+            {
+                const u64 y = sib[pos];
+                if (y > x || (odd && y == x)) pos += 1;
+            }
+            dst[(run >> 1) * 2 * L + i + pos] = x;
+        }
+        __syncthreads();
+        u64* t = src; src = dst; dst = t;
+    }
+    if (src != s_sort) {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) s_sort[EPT * tid + r] = src[EPT * tid + r];
+        __syncthreads();
+    }
 }
 
 // Pivot of one (image, class) from the keys of the SAMPLED tiles (first scatter launch), one warp
@@ -647,9 +676,10 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
         }
     }
     if (!sorted) {
-        if (P == kTopkThreads) block_bitonic_regs<1>(s_sort);
-        else if (P == 2 * kTopkThreads) block_bitonic_regs<2>(s_sort);
-        else if (P == 4 * kTopkThreads) block_bitonic_regs<4>(s_sort);
+        // s_list (2048 keys) is free by now: scratch of the merge sort
+        if (P == kTopkThreads) block_sort_desc<1>(s_sort, s_list);
+        else if (P == 2 * kTopkThreads) block_sort_desc<2>(s_sort, s_list);
+        else if (P == 4 * kTopkThreads) block_sort_desc<4>(s_sort, s_list);
         else block_bitonic_desc(s_sort, P);
     }
     // exact iff no pivot was used, or the K-th winner is above the pivot (every candidate above the
