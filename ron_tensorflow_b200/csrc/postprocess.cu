@@ -128,26 +128,28 @@ __device__ __forceinline__ void class_scan(const PostParams& p, const TileInfo& 
         const int ci = act ? cb + lane : 0;
         const float thr = act ? p.thr[seg0 + ci] : __int_as_float(0x7f800000);
         const float* col = s_cls + 1 + ci;
-        int cnt = 0;
-        for (int j = warp; j < nslots; j += kScatWarps) {
-            const int r = s_vrows[j];                  // warp-uniform; -1 = empty slot
-            if (r < 0) continue;
-            const int e = r * C;
-            const float v = (!TAIL || e + 1 + ci < wlim) ? col[e] : gcls[e + 1 + ci];
-            cnt += (v > thr) ? 1 : 0;
-        }
-        if (cnt == 0) continue;
-        u64* dst = p.keys + (seg0 + ci) * p.cap;
-        int pos = atomicAdd(p.counts + seg0 + ci, cnt);
-        for (int j = warp; j < nslots; j += kScatWarps) {
-            const int r = s_vrows[j];
-            if (r < 0) continue;
-            const int e = r * C;
-            const float v = (!TAIL || e + 1 + ci < wlim) ? col[e] : gcls[e + 1 + ci];
-            if (v > thr) {
-                dst[pos] = ((u64)__float_as_uint(v) << 32) | (u64)(nkey0 - (unsigned)r);
-                ++pos;
+        // pass 1: bit q of `hit` = this lane's class passes on the warp's q-th row (<= 32 rows per warp)
+        unsigned hit = 0u;
+        {
+            int q = 0;
+            for (int j = warp; j < nslots; j += kScatWarps, ++q) {
+                const int r = s_vrows[j];                  // warp-uniform; -1 = empty slot
+                if (r < 0) continue;
+                const int e = r * C;
+                const float v = (!TAIL || e + 1 + ci < wlim) ? col[e] : gcls[e + 1 + ci];
+                if (v > thr) hit |= 1u << q;
             }
+        }
+        if (hit == 0u) continue;
+        u64* dst = p.keys + (seg0 + ci) * p.cap + atomicAdd(p.counts + seg0 + ci, __popc(hit));
+        // pass 2: only the rows that passed
+        while (hit) {
+            const int q = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const int r = s_vrows[warp + q * kScatWarps];
+            const int e = r * C;
+            const float v = (!TAIL || e + 1 + ci < wlim) ? col[e] : gcls[e + 1 + ci];
+            *dst++ = ((u64)__float_as_uint(v) << 32) | (u64)(nkey0 - (unsigned)r);
         }
     }
 }
