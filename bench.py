@@ -396,6 +396,34 @@ def run_ours(args):
             'tpfp_gather': {'backend': 'nccl' if world > 1 else 'none', 'ms': gather_ms, 'mAP_voc07_synthetic': float(np.mean(aps)),
                             'records': int(sum(merged[c].scores.shape[0] for c in cls))},
         }
+    # ---------------------------------------------------------------- next row: ron_eval.py single image
+    roneval = None
+    if not args.no_postprocess:
+        from ron_tensorflow_b200 import ron_eval
+        import ron_tensorflow_b200.tf_extended as tfe2
+        ron_eval.FLAGS.select_threshold, ron_eval.FLAGS.objectness_thres = 0.02, 0.03
+        loc1, pred1, obj1 = synth.make_predictions(91, 1, N, N_CLASSES, hot=300)
+        ls1 = aset.layer_sizes
+        dP = [torch.from_numpy(t).to(dev) for t in synth.split_layers(pred1, ls1)]
+        dO = [torch.from_numpy(t).to(dev) for t in synth.split_layers(obj1, ls1)]
+        dL = [torch.from_numpy(t).to(dev) for t in synth.split_layers(loc1, ls1)]
+
+        def roneval_step():
+            bx = net.bboxes_decode(dL, anchors)
+            s_, l_, b_ = ron_eval.flaten_predict(dP, dO, bx)
+            b_ = tfe2.bboxes_clip([0., 0., 1., 1.], b_)
+            s_, l_, b_ = ron_eval.filter_boxes(s_, l_, b_, 0.03, (375, 500), [320., 320.])
+            s_, l_, b_ = ron_eval.tf_bboxes_nms(s_, l_, b_, nms_threshold=0.4, keep_top_k=20, mode='union')
+            return tfe2.bboxes_resize([0.1, 0.05, 0.9, 0.95], b_)
+
+        barrier()
+        ms_r = timed_steps(torch, roneval_step, args.steps, args.warmup)
+        barrier()
+        roneval = {'metric': 'images/sec (ron_eval.py single-image post-process)', 'value': world * 1e3 / float(np.mean(ms_r)),
+                   'unit': 'images/s', 'ms_per_step': float(np.mean(ms_r)), 'gpu_launches': timed_steps.launches,
+                   'config': {'workload': 'decode -> flaten_predict -> clip -> filter_boxes -> class-agnostic NMS (union, '
+                                          'keep 20) -> resize, one RON-320 image per step; shapes are data dependent, so '
+                                          'the chain reads 4 counts back to the host (latency bound)'}}
     clocks = sampler.stop()
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
@@ -426,7 +454,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(enc_d2h)},
             'gpu_launches': int(enc_launches),
             'clocks': clocks,
-            'stages': {'encode_b256': enc256, 'postprocess': post},
+            'stages': {'encode_b256': enc256, 'postprocess': post, 'ron_eval_single_image': roneval},
         }
         print_line(json.dumps(line))
     if world > 1:

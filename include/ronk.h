@@ -202,6 +202,29 @@ size_t ronk_dual_max_match_workspace_bytes(int G);
 int ronk_dual_max_match(const float* overlap, int G, int N, float high_thres, float low_thres, int match_flags,
                         int64_t* out_matched, float* out_scores, void* ws, void* stream);
 
+/* ------------------------------------------- ron_eval.py single-image variant
+ * (the heavy steps reuse ronk_sort_topk + ronk_nms_batch, mode 'union')
+ * ronk_flaten_predict     flaten_predict            ron_eval.py:111-144   per-layer pred [n_l,C], objness [n_l]
+ *                         -> scores = objness * pred [N,C], labels = first arg-max int64 [N],
+ *                            mask uint8 [N] = (label > 0) & (objness > threshold)   (batch size 1, like the reference)
+ * ronk_filter_boxes_mask  filter_boxes              ron_eval.py:369-392   keep mask of boxes [n,4]
+ * ronk_rowmax_mask        reduce_max + threshold    ron_eval.py:149-151   scores [n,C] -> max [n], mask [n]
+ * ronk_compact_indices    tf.boolean_mask           order-preserving: indices of the set mask bytes + their count
+ * ronk_gather_rows        tf.boolean_mask / gather  dst[i] = src[idx[i]] for rows of row_bytes (multiple of 4)
+ * ronk_bboxes_resize      tfe.bboxes_resize         tf_extended/bboxes.py:147-171   (box - v) / s, bbox_ref on the host
+ */
+int ronk_flaten_predict(const float* const* pred_layers_host, const float* const* obj_layers_host,
+                        const int* layer_sizes_host, int num_layers, int C, float objectness_threshold,
+                        float* out_scores, int64_t* out_labels, uint8_t* out_mask, void* stream);
+int ronk_filter_boxes_mask(const float* boxes, int n, float min_size, uint8_t* out_mask, void* stream);
+int ronk_rowmax_mask(const float* scores, int n, int C, float threshold, float* out_max, uint8_t* out_mask,
+                     void* stream);
+size_t ronk_compact_workspace_bytes(int n);
+int ronk_compact_indices(const uint8_t* mask, int n, int32_t* out_idx, int32_t* out_count, void* ws, void* stream);
+int ronk_gather_rows(const void* src, int row_bytes, const int32_t* idx, int m, void* dst, void* stream);
+int ronk_bboxes_resize(const float* bbox_ref_host /*[4]*/, const float* boxes, long long n, float* out_boxes,
+                       void* stream);
+
 /* number of kernel launches issued by this library in this process since load
  * (bench.py reports it as gpu_launches) */
 long long ronk_launch_count(void);

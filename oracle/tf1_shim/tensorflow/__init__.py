@@ -287,6 +287,11 @@ def log(x, name=None): return _f64_round(np.log, x)
 def exp(x, name=None): return _f64_round(np.exp, x)
 
 
+def sqrt(x, name=None):
+    """IEEE square root is correctly rounded in every implementation: one float32 rounding."""
+    return Tensor(np.sqrt(_v(x)))
+
+
 def cast(x, dtype, name=None):
     return Tensor(_v(x).astype(_npdt(dtype)))
 

@@ -53,6 +53,14 @@ SIGNATURES = {
     'ronk_dual_max_match_workspace_bytes': (c_size_t, [c_int]),
     'ronk_dual_max_match': (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    'ronk_flaten_predict': (c_int, [P(c_void_p), P(c_void_p), P(c_int), c_int, c_int, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    'ronk_filter_boxes_mask': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    'ronk_rowmax_mask': (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    'ronk_compact_workspace_bytes': (c_size_t, [c_int]),
+    'ronk_compact_indices': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ronk_gather_rows': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'ronk_bboxes_resize': (c_int, [P(c_float), c_void_p, c_longlong, c_void_p, c_void_p]),
     'ronk_tpfp_match': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -435,3 +435,81 @@ def overlap_ref(bbox_ref, boxes, what):
         _ffi.check(_ffi.lib().ronk_overlap_ref(_ptr(r), int(r.shape[0]), _ptr(b), int(b.shape[0]),
                                                0 if what == 'jaccard' else 1, _ptr(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- ron_eval.py variant
+def compact_indices(mask):
+    """tf.boolean_mask as indices: order-preserving positions of the set bytes of ``mask`` (uint8 [n]).
+    Returns an int32 CUDA tensor of length count (one device->host read of the count: the result has a
+    data-dependent shape, exactly like the reference's boolean_mask)."""
+    n = int(mask.numel())
+    idx = torch.empty((max(n, 1),), dtype=torch.int32, device=mask.device)
+    cnt = torch.empty((1,), dtype=torch.int32, device=mask.device)
+    L = _ffi.lib()
+    ws = _workspace('cmp', L.ronk_compact_workspace_bytes(n), False, mask.device)
+    with torch.cuda.device(mask.device):
+        _ffi.check(L.ronk_compact_indices(_ptr(mask), n, _ptr(idx), _ptr(cnt), _ptr(ws), _stream()))
+    return idx[:int(cnt.item())]
+
+
+def gather_rows(src, idx):
+    """src[idx] along axis 0 for a contiguous tensor whose rows are multiples of 4 bytes."""
+    src = src.contiguous()
+    m = int(idx.numel())
+    row_bytes = int(np.prod(src.shape[1:], dtype=np.int64)) * src.element_size()
+    out = torch.empty((m,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        _ffi.check(_ffi.lib().ronk_gather_rows(_ptr(src), int(row_bytes), _ptr(idx), m, _ptr(out), _stream()))
+    return out
+
+
+def flaten_predict(pred_layers, obj_layers, objectness_threshold):
+    """ron_eval.py:111-144 up to the mask: returns scores [N,C] (objness * pred), labels int64 [N], mask uint8 [N]."""
+    _require_cuda()
+    ps = [as_cuda(t, torch.float32) for t in pred_layers]
+    dev = ps[0].device
+    C = int(ps[0].shape[-1])
+    os_ = [as_cuda(t, torch.float32, dev) for t in obj_layers]
+    sizes = [int(t.numel() // C) for t in ps]
+    for t, o, n in zip(ps, os_, sizes):
+        if int(o.numel()) != n:
+            raise ValueError('objness and predictions disagree on the number of anchors')
+    N = sum(sizes)
+    scores = torch.empty((N, C), dtype=torch.float32, device=dev)
+    labels = torch.empty((N,), dtype=torch.int64, device=dev)
+    mask = torch.empty((N,), dtype=torch.uint8, device=dev)
+    pp = (ctypes.c_void_p * len(ps))(*[t.data_ptr() for t in ps])
+    op = (ctypes.c_void_p * len(ps))(*[t.data_ptr() for t in os_])
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.lib().ronk_flaten_predict(pp, op, _ffi.iarr(sizes), len(ps), C, float(objectness_threshold),
+                                                  _ptr(scores), _ptr(labels), _ptr(mask), _stream()))
+    return scores, labels, mask
+
+
+def filter_boxes_mask(boxes, min_size):
+    b = as_cuda(boxes, torch.float32).reshape(-1, 4)
+    mask = torch.empty((b.shape[0],), dtype=torch.uint8, device=b.device)
+    with torch.cuda.device(b.device):
+        _ffi.check(_ffi.lib().ronk_filter_boxes_mask(_ptr(b), int(b.shape[0]), float(min_size), _ptr(mask), _stream()))
+    return mask
+
+
+def rowmax_mask(scores, threshold):
+    s = as_cuda(scores, torch.float32)
+    n, C = int(s.shape[0]), int(s.shape[1])
+    out = torch.empty((n,), dtype=torch.float32, device=s.device)
+    mask = torch.empty((n,), dtype=torch.uint8, device=s.device)
+    with torch.cuda.device(s.device):
+        _ffi.check(_ffi.lib().ronk_rowmax_mask(_ptr(s), n, C, float(threshold), _ptr(out), _ptr(mask), _stream()))
+    return out, mask
+
+
+def bboxes_resize(bbox_ref, boxes):
+    b = as_cuda(boxes, torch.float32)
+    if b.shape[-1] != 4:
+        raise ValueError('boxes must be [..., 4]')
+    ref = [float(v) for v in (bbox_ref.tolist() if hasattr(bbox_ref, 'tolist') else bbox_ref)]
+    out = torch.empty_like(b)
+    with torch.cuda.device(b.device):
+        _ffi.check(_ffi.lib().ronk_bboxes_resize(_ffi.farr(ref), _ptr(b), b.numel() // 4, _ptr(out), _stream()))
+    return out

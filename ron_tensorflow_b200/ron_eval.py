@@ -1,0 +1,71 @@
+"""Drop-in for the post-process functions of the reference's ``ron_eval.py`` (single-image
+evaluation): ``flaten_predict`` :111-144, ``filter_boxes`` :369-392,
+the class-agnostic ``tf_bboxes_nms`` :146-210 -- same names, argument order and defaults.  The
+thresholds the reference reads from ``tf.app.flags.FLAGS`` live in the module-level ``FLAGS``
+object below (same names and defaults, ron_eval.py:82-91).
+
+All results have data-dependent shapes (``tf.boolean_mask``); every function returns CUDA
+tensors trimmed to their real length (one device->host read of the count per mask).
+"""
+import numpy as np
+import torch
+
+from . import core
+
+
+class _Flags(object):
+    select_threshold = 0.6       # ron_eval.py:82-83
+    nms_threshold = 0.4          # :84-85
+    objectness_thres = 0.95      # :86-87
+    nms_topk_percls = 10         # :88-89
+    nms_topk = 20                # :90-91
+
+
+FLAGS = _Flags()
+
+
+def flaten_predict(predictions, objness_pred, localisations):
+    """reference ron_eval.py:111-144.  Lists over layers of [1,H,W,A,C] / [1,H,W,A,1] / [1,H,W,A,4]
+    (``localisations`` are decoded boxes).  Returns scores [M,C] = objness * predictions, labels int64 [M]
+    (arg-max class), boxes [M,4] for the anchors whose label is not background and whose objectness exceeds
+    FLAGS.objectness_thres, in anchor order."""
+    if int(predictions[0].shape[0]) > 1:
+        raise ValueError('only batch_size 1 is supported.')
+    scores, labels, mask = core.flaten_predict(predictions, objness_pred, FLAGS.objectness_thres)
+    boxes = torch.cat([core.as_cuda(t, torch.float32, scores.device).reshape(-1, 4) for t in localisations], 0)
+    idx = core.compact_indices(mask)
+    return core.gather_rows(scores, idx), core.gather_rows(labels, idx), core.gather_rows(boxes, idx)
+
+
+def filter_boxes(scores, labels, bboxes, min_size_ratio, image_shape, net_input_shape):
+    """reference ron_eval.py:369-392: keep boxes with both sides > min_size and the centre inside the image."""
+    # :374, float32 like the TF graph: max(0.0001, ratio * sqrt(float(h * w) / (net_h * net_w)))
+    area = np.float32(int(image_shape[0]) * int(image_shape[1]))
+    min_size = np.maximum(np.float32(0.0001),
+                          np.float32(min_size_ratio) * np.sqrt(area / np.float32(net_input_shape[0] * net_input_shape[1])))
+    b = core.as_cuda(bboxes, torch.float32).reshape(-1, 4)
+    idx = core.compact_indices(core.filter_boxes_mask(b, float(min_size)))
+    return (core.gather_rows(core.as_cuda(scores, torch.float32, b.device), idx),
+            core.gather_rows(core.as_cuda(labels, torch.int64, b.device), idx), core.gather_rows(b, idx))
+
+
+def tf_bboxes_nms(scores, labels, bboxes, nms_threshold=0.5, keep_top_k=200, mode='union', scope=None):
+    """reference ron_eval.py:146-210: class-agnostic greedy NMS on the best class score of every box.
+    scores [M,C]; returns the kept (score [k], label [k], box [k,4]) in decreasing score order."""
+    if mode not in ('union', 'min'):
+        raise ValueError('unknown mode to use for nms.')
+    s = core.as_cuda(scores, torch.float32)
+    best, mask = core.rowmax_mask(s, FLAGS.select_threshold)                      # :149-151
+    idx = core.compact_indices(mask)
+    best = core.gather_rows(best, idx)
+    labels = core.gather_rows(core.as_cuda(labels, torch.int64, s.device), idx)
+    bboxes = core.gather_rows(core.as_cuda(bboxes, torch.float32, s.device).reshape(-1, 4), idx)
+    n = int(best.shape[0])
+    if n < 1:                                                                       # tf.cond(num_anchors < 1, ...) :210
+        return best, labels, bboxes
+    ss, sb, si = core.sort_topk(best.reshape(1, n), bboxes.reshape(1, n, 4), n, want_idx=True)    # :155-156
+    ns, nb, ni = core.nms_batch(ss, sb, nms_threshold, keep_top_k, mode, assume_sorted=True, want_idx=True)
+    kept = core.compact_indices((ni[0] >= 0).to(torch.uint8))
+    pos = core.gather_rows(ni[0].contiguous(), kept)                # positions in the sorted list
+    src = core.gather_rows(si[0].contiguous(), pos)                 # positions before sorting
+    return core.gather_rows(ns[0].contiguous(), kept), core.gather_rows(labels, src), core.gather_rows(nb[0].contiguous(), kept)

@@ -34,15 +34,10 @@ def bboxes_clip(bbox_ref, bboxes, scope=None):
 
 
 def bboxes_resize(bbox_ref, bboxes, name=None):
-    """reference :147-171: translate by the reference corner, scale by its size (elementwise
-    plumbing after cropping; not on the detection hot path)."""
+    """reference :147-171: translate by the reference corner, then divide by its size."""
     if isinstance(bboxes, dict):
         return {c: bboxes_resize(bbox_ref, bboxes[c]) for c in bboxes.keys()}
-    b = core.as_cuda(bboxes, torch.float32)
-    r = torch.as_tensor([float(v) for v in bbox_ref], dtype=torch.float32, device=b.device)
-    v = torch.stack([r[0], r[1], r[0], r[1]])
-    s = torch.stack([r[2] - r[0], r[3] - r[1], r[2] - r[0], r[3] - r[1]])
-    return (b - v) / s
+    return core.bboxes_resize(bbox_ref, bboxes)
 
 
 def bboxes_nms(scores, bboxes, nms_threshold=0.5, keep_top_k=200, mode='min', scope=None):

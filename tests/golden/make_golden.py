@@ -262,7 +262,50 @@ def gen_tpfp():
     save('tpfp', **out)
 
 
+# --------------------------------------------------------------------------- #
+# ron_eval.py single-image variant.  ron_eval.py cannot be imported as a module (scipy.misc.imread,
+# dataset / slim imports, flag definitions at import time), so the UNMODIFIED source of the four
+# functions is cut out of the file with ``ast`` and executed over the same TF-1 shim.
+# --------------------------------------------------------------------------- #
+def gen_ron_eval():
+    import ast
+    src = open(os.path.join(REF, 'ron_eval.py')).read()
+    want = {'flaten_predict', 'tf_bboxes_nms', 'filter_boxes'}
+    body = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want]
+
+    class F(object):
+        select_threshold, nms_threshold, objectness_thres, nms_topk = 0.02, 0.4, 0.03, 20
+    ns = {'tf': tf, 'tfe': tfe, 'np': np, 'FLAGS': F}
+    exec(compile(ast.Module(body=body, type_ignores=[]), 'ron_eval.py', 'exec'), ns)
+    out = {}
+    net = ron_vgg_320.RONNet()
+    anchors = net.anchors(net.params.img_shape)
+    LS, FS = [250, 1000, 4000, 16000], [(5, 5), (10, 10), (20, 20), (40, 40)]
+    for tag, seed, hot, keep, mode, img in (('a', 91, 300, 20, 'union', (375, 500)), ('b', 92, 40, 200, 'min', (500, 333))):
+        loc, pred, obj = synth.make_predictions(seed, 1, 21250, 21, hot=hot)
+        P = [T(t) for t in synth.split_layers(pred, LS, FS, [10] * 4)]
+        Ob = [T(t) for t in synth.split_layers(obj[..., None], LS, FS, [10] * 4)]
+        Lc = [T(t) for t in synth.split_layers(loc, LS, FS, [10] * 4)]
+        Bx = net.bboxes_decode(Lc, anchors)
+        s, l, b = ns['flaten_predict'](P, Ob, Bx)
+        out[tag + '_flat_scores'], out[tag + '_flat_labels'], out[tag + '_flat_boxes'] = npy(s), npy(l), npy(b)
+        bbox_img = np.array([0., 0., 1., 1.], np.float32)
+        b = tfe.bboxes.bboxes_clip(T(bbox_img), b)
+        s, l, b = ns['filter_boxes'](s, l, b, 0.03, T(np.array(img, np.int32)), [320., 320.])
+        out[tag + '_filt_scores'], out[tag + '_filt_labels'], out[tag + '_filt_boxes'] = npy(s), npy(l), npy(b)
+        s, l, b = ns['tf_bboxes_nms'](s, l, b, nms_threshold=F.nms_threshold, keep_top_k=keep, mode=mode)
+        out[tag + '_nms_scores'], out[tag + '_nms_labels'], out[tag + '_nms_boxes'] = npy(s), npy(l), npy(b)
+        ref = np.array([0.1, 0.05, 0.9, 0.95], np.float32)
+        out[tag + '_resized'] = npy(tfe.bboxes.bboxes_resize(T(ref), b))
+        out[tag + '_cfg'] = np.array([seed, hot, keep, mode == 'union', img[0], img[1]], np.int64)
+        out[tag + '_in_pred_sha'] = np.frombuffer(__import__('hashlib').sha256(pred.tobytes()).digest(), np.uint8)
+    save('ron_eval', **out)
+
+
 if __name__ == '__main__':
+    gen_ron_eval()
+    if '--only-ron-eval' in sys.argv:
+        sys.exit(0)
     gen_anchors()
     gen_encode()
     gen_postprocess()

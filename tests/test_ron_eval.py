@@ -1,0 +1,97 @@
+"""ron_eval.py single-image post-process variant: flaten_predict ->
+clip -> filter_boxes -> class-agnostic tf_bboxes_nms -> bboxes_resize.  The golden fixture was made
+by the reference's own function source executed over the TF-1 shim (tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import ron_oracle as O
+from ron_tensorflow_b200 import synth
+from _util import need_cuda, eq
+
+LS = [250, 1000, 4000, 16000]
+FS = [(5, 5), (10, 10), (20, 20), (40, 40)]
+SEL, OBJ, NMS = 0.02, 0.03, 0.4
+
+
+def _inputs(g, tag):
+    seed, hot, keep, union, ih, iw = [int(v) for v in g[tag + '_cfg']]
+    loc, pred, obj = synth.make_predictions(seed, 1, 21250, 21, hot=hot)
+    if hashlib.sha256(pred.tobytes()).digest() != g[tag + '_in_pred_sha'].tobytes():
+        pytest.skip('numpy Generator stream differs from the one that made the fixture')
+    return loc, pred, obj, keep, ('union' if union else 'min'), (ih, iw)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_oracle_matches_reference_functions(golden, tag):
+    g = golden('ron_eval')
+    loc, pred, obj, keep, mode, img = _inputs(g, tag)
+    dec = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+    boxes = O.decode(loc[0], dec)
+    s, l, b = O.flaten_predict([pred[0]], [obj[0]], [boxes], OBJ)
+    assert np.array_equal(s, g[tag + '_flat_scores']) and np.array_equal(l, g[tag + '_flat_labels'])
+    assert np.array_equal(b, g[tag + '_flat_boxes'])
+    b = O.clip_boxes([0., 0., 1., 1.], b)
+    s, l, b = O.filter_boxes(s, l, b, 0.03, img, [320., 320.])
+    assert np.array_equal(s, g[tag + '_filt_scores']) and np.array_equal(b, g[tag + '_filt_boxes'])
+    s, l, b = O.bboxes_nms_agnostic(s, l, b, SEL, NMS, keep, mode)
+    assert np.array_equal(s, g[tag + '_nms_scores']) and np.array_equal(l, g[tag + '_nms_labels'])
+    assert np.array_equal(b, g[tag + '_nms_boxes'])
+    assert np.array_equal(O.bboxes_resize([0.1, 0.05, 0.9, 0.95], b), g[tag + '_resized'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_cuda_matches_reference_functions(golden, tag):
+    need_cuda()
+    from ron_tensorflow_b200 import ron_eval
+    from ron_tensorflow_b200.nets import ron_vgg_320
+    import ron_tensorflow_b200.tf_extended as tfe
+    g = golden('ron_eval')
+    loc, pred, obj, keep, mode, img = _inputs(g, tag)
+    net = ron_vgg_320.RONNet()
+    anchors = net.anchors(net.params.img_shape)
+    P = synth.split_layers(pred, LS, FS, [10] * 4)
+    Ob = synth.split_layers(obj[..., None], LS, FS, [10] * 4)
+    Lc = synth.split_layers(loc, LS, FS, [10] * 4)
+    ron_eval.FLAGS.select_threshold, ron_eval.FLAGS.objectness_thres = SEL, OBJ
+    boxes = net.bboxes_decode(Lc, anchors)
+    s, l, b = ron_eval.flaten_predict(P, Ob, boxes)
+    eq(s, g[tag + '_flat_scores'], 'flat scores'); eq(l, g[tag + '_flat_labels'], 'flat labels'); eq(b, g[tag + '_flat_boxes'], 'flat boxes')
+    b = tfe.bboxes_clip([0., 0., 1., 1.], b)
+    s, l, b = ron_eval.filter_boxes(s, l, b, 0.03, img, [320., 320.])
+    eq(s, g[tag + '_filt_scores'], 'filtered scores'); eq(l, g[tag + '_filt_labels'], 'filtered labels'); eq(b, g[tag + '_filt_boxes'], 'filtered boxes')
+    s, l, b = ron_eval.tf_bboxes_nms(s, l, b, nms_threshold=NMS, keep_top_k=keep, mode=mode)
+    eq(s, g[tag + '_nms_scores'], 'nms scores'); eq(l, g[tag + '_nms_labels'], 'nms labels'); eq(b, g[tag + '_nms_boxes'], 'nms boxes')
+    eq(tfe.bboxes_resize([0.1, 0.05, 0.9, 0.95], b), g[tag + '_resized'], 'resized')
+
+
+@pytest.mark.gpu
+def test_cuda_vs_oracle_dense_and_empty():
+    """Dense scores (thousands of survivors: compaction across many tiles, sort of ~8k boxes) and the
+    empty case (nothing passes: every stage must return zero-length tensors)."""
+    need_cuda()
+    import torch
+    from ron_tensorflow_b200 import ron_eval
+    from ron_tensorflow_b200.nets import ron_vgg_320
+    net = ron_vgg_320.RONNet()
+    anchors = net.anchors(net.params.img_shape)
+    dec = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+    loc, pred, obj = synth.make_predictions(404, 1, 21250, 21, hot=300, dense=True)
+    boxes = O.decode(loc[0], dec)
+    P = synth.split_layers(pred, LS); Ob = synth.split_layers(obj[..., None], LS); Bx = synth.split_layers(boxes[None], LS)
+    ron_eval.FLAGS.select_threshold, ron_eval.FLAGS.objectness_thres = 0.002, 0.03
+    s, l, b = ron_eval.flaten_predict(P, Ob, [torch.from_numpy(t) for t in Bx])
+    os_, ol, ob = O.flaten_predict([pred[0]], [obj[0]], [boxes], 0.03)
+    assert os_.shape[0] > 5000
+    eq(s, os_, 'scores'); eq(l, ol, 'labels'); eq(b, ob, 'boxes')
+    s, l, b = ron_eval.tf_bboxes_nms(s, l, b, nms_threshold=0.45, keep_top_k=300, mode='union')
+    os_, ol, ob = O.bboxes_nms_agnostic(os_, ol, ob, 0.002, 0.45, 300, 'union')
+    eq(s, os_, 'nms scores'); eq(l, ol, 'nms labels'); eq(b, ob, 'nms boxes')
+    ron_eval.FLAGS.objectness_thres = 2.0                       # nothing passes
+    s, l, b = ron_eval.flaten_predict(P, Ob, [torch.from_numpy(t) for t in Bx])
+    assert s.shape == (0, 21) and l.shape == (0,) and b.shape == (0, 4)
+    s, l, b = ron_eval.filter_boxes(s, l, b, 0.03, (375, 500), [320., 320.])
+    s, l, b = ron_eval.tf_bboxes_nms(s, l, b)
+    assert s.shape == (0,) and l.shape == (0,) and b.shape == (0, 4)
