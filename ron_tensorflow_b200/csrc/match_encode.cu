@@ -391,7 +391,7 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
 }
 
 // grid (B, items): blockIdx.y walks the handle's work-item table (heavy, coarse-layer items first)
-__global__ void __launch_bounds__(kEncThreads, 10)
+__global__ void __launch_bounds__(kEncThreads, 8)
 match_encode_kernel(const __grid_constant__ EncodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int4 item = __ldg(p.items + blockIdx.y);

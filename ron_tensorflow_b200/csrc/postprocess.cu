@@ -600,7 +600,7 @@ __device__ int rebuild_list(const PostParams& p, int b, int c, u64* g, int* s_cn
 //                     the keys >= pivot in shared memory, and the select runs on those.  If the pivot
 //                     turns out too high (fewer than K survivors) or too low (more than 2048), the
 //                     generic 8-bit radix select over the whole list takes over -- always exact.
-__global__ void __launch_bounds__(kTopkThreads, 4)
+__global__ void __launch_bounds__(kTopkThreads, 6)
 select_topk_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = next_pow2(p.K);
@@ -855,7 +855,7 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     int per_sm = (int)((220 * 1024) / (smem_a + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
-    // Two scatter launches when the lists would be much longer than K: first a spread-out eighth of
+    // Two scatter launches when the lists would be much longer than K: first a spread-out sixteenth of
     // every image's tiles (threshold sel_thr), then a per-(image, class) pivot from those keys,
     // then all other tiles with the pivot as threshold.  perm_mul ~ 0.618 * tiles, coprime.
     const int tpi = toff;
@@ -864,7 +864,8 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     p.pivot_rank = 0;
     p.force_rebuild = (select_flags & RONK_SELECT_TEST_REBUILD) ? 1 : 0;
     if (!(select_flags & RONK_SELECT_NO_SAMPLING) && tpi >= 16 && (long long)K * 8 <= h->tab.N) {
-        tpi1 = tpi / 8;
+        tpi1 = tpi / 16;                 // a sixteenth of the tiles: pivot rank mu + 4 sigma + 8 still leaves ~2K keys per list
+        if (tpi1 < 2) tpi1 = 2;
         if (tpi1 > 16) tpi1 = 16;
         int m = (int)(0.618 * tpi);
         auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
