@@ -20,7 +20,7 @@
 
 namespace ronk {
 
-constexpr int kTileRows = 256;
+constexpr int kTileRows = 128;
 
 struct PostParams {
     LayerTable tab;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void class_scan(const PostParams& p, const TileInfo& 
 //     localisation rows that arrived with the same TMA transaction as the scores, and stores the
 //     box to the per-image box table (the top-k kernel gathers its winners from it);
 //  C. class scan (class_scan above): lane = class, the 8 warps share the surviving valid rows.
-__global__ void __launch_bounds__(kTileRows, 4)
+__global__ void __launch_bounds__(kTileRows, 8)
 scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int C = p.C;
