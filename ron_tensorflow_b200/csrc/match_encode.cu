@@ -206,6 +206,7 @@ __device__ __forceinline__ void sweep(const float4* s_box, const float* s_area, 
                     for (int j = kEncApt - 1; j >= 0; --j)
                         if (bits[q][j] == m) cand = (unsigned)(j * 32 + lane);
                     const unsigned first = __reduce_min_sync(full, cand);
+                    __syncwarp();                       // every lane has consumed its read of s_best (cur) above
                     if (lane == 0) {
                         u64 key = ((u64)m << 32) | (u64)(0xffffffffu - (set_c0 + first));
                         if (key > s_best[gq[q]]) s_best[gq[q]] = key;       // private to this warp: no atomic
