@@ -208,6 +208,7 @@ int ronk_dual_max_match(const float* overlap, int G, int N, float high_thres, fl
  *                         -> scores = objness * pred [N,C], labels = first arg-max int64 [N],
  *                            mask uint8 [N] = (label > 0) & (objness > threshold)   (batch size 1, like the reference)
  * ronk_filter_boxes_mask  filter_boxes              ron_eval.py:369-392   keep mask of boxes [n,4]
+ * ronk_minsize_mask       RONNet.bboxes_filter_min  nets/ron_vgg_320.py:222-228   (w > minsize) & (h > minsize)
  * ronk_rowmax_mask        reduce_max + threshold    ron_eval.py:149-151   scores [n,C] -> max [n], mask [n]
  * ronk_compact_indices    tf.boolean_mask           order-preserving: indices of the set mask bytes + their count
  * ronk_gather_rows        tf.boolean_mask / gather  dst[i] = src[idx[i]] for rows of row_bytes (multiple of 4)
@@ -217,6 +218,7 @@ int ronk_flaten_predict(const float* const* pred_layers_host, const float* const
                         const int* layer_sizes_host, int num_layers, int C, float objectness_threshold,
                         float* out_scores, int64_t* out_labels, uint8_t* out_mask, void* stream);
 int ronk_filter_boxes_mask(const float* boxes, int n, float min_size, uint8_t* out_mask, void* stream);
+int ronk_minsize_mask(const float* boxes, int n, float min_size, uint8_t* out_mask, void* stream);
 int ronk_rowmax_mask(const float* scores, int n, int C, float threshold, float* out_max, uint8_t* out_mask,
                      void* stream);
 size_t ronk_compact_workspace_bytes(int n);

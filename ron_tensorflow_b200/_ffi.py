@@ -56,6 +56,7 @@ SIGNATURES = {
     'ronk_flaten_predict': (c_int, [P(c_void_p), P(c_void_p), P(c_int), c_int, c_int, c_float, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),
     'ronk_filter_boxes_mask': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    'ronk_minsize_mask': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
     'ronk_rowmax_mask': (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'ronk_compact_workspace_bytes': (c_size_t, [c_int]),
     'ronk_compact_indices': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

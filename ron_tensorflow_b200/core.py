@@ -494,6 +494,14 @@ def filter_boxes_mask(boxes, min_size):
     return mask
 
 
+def minsize_mask(boxes, min_size):
+    b = as_cuda(boxes, torch.float32).reshape(-1, 4)
+    mask = torch.empty((b.shape[0],), dtype=torch.uint8, device=b.device)
+    with torch.cuda.device(b.device):
+        _ffi.check(_ffi.lib().ronk_minsize_mask(_ptr(b), int(b.shape[0]), float(min_size), _ptr(mask), _stream()))
+    return mask
+
+
 def rowmax_mask(scores, threshold):
     s = as_cuda(scores, torch.float32)
     n, C = int(s.shape[0]), int(s.shape[1])

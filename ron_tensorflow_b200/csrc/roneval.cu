@@ -60,6 +60,15 @@ box_filter_kernel(const float4* __restrict__ boxes, int n, float min_size, uint8
     mask[i] = (ws > min_size && hs > min_size && x_ctr > 0.f && y_ctr > 0.f && x_ctr < 1.f && y_ctr < 1.f) ? 1 : 0;
 }
 
+// RONNet.bboxes_filter_min (nets/ron_vgg_320.py:222-228): width > minsize and height > minsize
+__global__ void __launch_bounds__(256)
+minsize_mask_kernel(const float4* __restrict__ boxes, int n, float min_size, uint8_t* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = boxes[i];
+    mask[i] = ((b.w - b.y) > min_size && (b.z - b.x) > min_size) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256)
 rowmax_mask_kernel(const float* __restrict__ scores, int n, int C, float thr, float* __restrict__ out,
                    uint8_t* __restrict__ mask) {
@@ -194,6 +203,15 @@ extern "C" int ronk_filter_boxes_mask(const float* boxes, int n, float min_size,
     RONK_REQUIRE(boxes && out_mask && ((uintptr_t)boxes % 16) == 0, RONK_EINVAL,
                  "ronk_filter_boxes_mask: bad argument");
     box_filter_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, n, min_size, out_mask);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_minsize_mask(const float* boxes, int n, float min_size, uint8_t* out_mask, void* stream) {
+    RONK_REQUIRE(n >= 0, RONK_EINVAL, "ronk_minsize_mask: bad argument");
+    if (n == 0) return RONK_OK;
+    RONK_REQUIRE(boxes && out_mask && ((uintptr_t)boxes % 16) == 0, RONK_EINVAL, "ronk_minsize_mask: bad argument");
+    minsize_mask_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, n, min_size, out_mask);
     RONK_LAUNCHED();
     return RONK_OK;
 }

@@ -133,18 +133,19 @@ class RONNet(object):
             return d_scores, d_bboxes
         s = core.as_cuda(scores, torch.float32)
         b = core.as_cuda(bboxes, torch.float32, s.device)
-        # host-side compaction (dynamic shapes); the fused path (detected_bboxes / detect) never
-        # materialises this tensor -- the size test lives inside the select kernel.
-        h = b[..., 2] - b[..., 0]
-        w = b[..., 3] - b[..., 1]
-        mask = (w > np.float32(minsize)) & (h > np.float32(minsize))
-        width = max(int(mask.sum(-1).max().item()), int(top_k))
+        # per image: size mask kernel -> order-preserving compaction -> row gather (dynamic shapes, like
+        # tf.boolean_mask); the fused path (detected_bboxes / detect) never materialises this tensor --
+        # the size test lives inside the select kernel.
+        kept = []
+        for i in range(s.shape[0]):
+            idx = core.compact_indices(core.minsize_mask(b[i], np.float32(minsize)))
+            kept.append((core.gather_rows(s[i].contiguous(), idx), core.gather_rows(b[i].contiguous(), idx)))
+        width = max(max(int(k[0].shape[0]) for k in kept), int(top_k))          # pad_axis to >= top_k (:230-231)
         os_ = torch.zeros((s.shape[0], width), dtype=torch.float32, device=s.device)
         ob = torch.zeros((s.shape[0], width, 4), dtype=torch.float32, device=s.device)
-        for i in range(s.shape[0]):
-            k = int(mask[i].sum().item())
-            os_[i, :k] = s[i][mask[i]]
-            ob[i, :k] = b[i][mask[i]]
+        for i, (ks, kb) in enumerate(kept):
+            os_[i, :ks.shape[0]] = ks
+            ob[i, :ks.shape[0]] = kb
         return os_, ob
 
     # ------------------------------------------------------------------ detect
