@@ -403,7 +403,8 @@ __device__ __forceinline__ void block_bitonic_desc(u64* s_sort, int P) {
     }
 }
 
-// Sort of s_sort[0..P), P = 256 * EPT, descending, distinct keys (zeros allowed, they end up last):
+// Sort of s_sort[0..P), P = 256 * EPT, descending, ALL KEYS DISTINCT (empty slots hold distinct
+// small values with a zero high word, see select_topk_kernel):
 //  A. every warp sorts its run of 32 * EPT consecutive elements in registers (bitonic network, warp
 //     shuffles, no barrier);
 //  B. log2(8) merge levels: each element finds its rank in the sibling run with a branch-free binary
@@ -460,19 +461,12 @@ __device__ __forceinline__ void block_sort_desc(u64* s_sort, u64* s_tmp) {
             const u64 x = src[e];
             const int run = e / L, i = e & (L - 1);
             const u64* sib = src + (run ^ 1) * L;
-            const bool odd = run & 1;
-            // number of sibling elements that precede x in the merged (descending) order:
-            // y > x, and y == x too when the sibling is the left run (only zeros can be equal)
+            // number of sibling elements that precede x in the merged (descending) order
             int pos = 0;
 #pragma unroll
-            for (int st = L >> 1; st > 0; st >>= 1) {
-                const u64 y = sib[pos + st - 1];
-                if (y > x || (odd && y == x)) pos += st;
-            }
-            {
-                const u64 y = sib[pos];
-                if (y > x || (odd && y == x)) pos += 1;
-            }
+            for (int st = L >> 1; st > 0; st >>= 1)
+                if (sib[pos + st - 1] > x) pos += st;
+            if (sib[pos] > x) pos += 1;
             dst[(run >> 1) * 2 * L + i + pos] = x;
         }
         __syncthreads();
@@ -618,7 +612,9 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
     u64* g = p.keys + (size_t)seg * p.cap;
     const float seg_thr = p.thr[seg];
     for (int attempt = 0;; ++attempt) {
-    for (int i = tid; i < P; i += kTopkThreads) s_sort[i] = 0ull;
+    // empty slots: distinct keys with a zero high word (a real key has score bits > 0 there), so the
+    // sort never sees equal keys and the slots end up last
+    for (int i = tid; i < P; i += kTopkThreads) s_sort[i] = (u64)(P - i);
     if (tid == 0) { s_cnt = 0; s_ctl[3] = 0; }
     __syncthreads();
 
@@ -688,7 +684,7 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
     // pivot is in the list).  Otherwise rebuild the list from the inputs and select again.
     if (attempt > 0 || !(seg_thr > p.sel_thr)) break;
     const u64 kth = s_sort[p.K - 1];
-    if (kth != 0ull && __uint_as_float((unsigned)(kth >> 32)) > seg_thr && !p.force_rebuild) break;
+    if ((kth >> 32) != 0ull && __uint_as_float((unsigned)(kth >> 32)) > seg_thr && !p.force_rebuild) break;
     __syncthreads();
     n = rebuild_list(p, b, seg - b * CM + 1, g, &s_cnt);
     n = n > p.cap ? p.cap : n;
@@ -698,7 +694,7 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
         float sc = 0.f;
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         int idx = -1;
-        if (k != 0ull) {
+        if ((k >> 32) != 0ull) {                 // real key (empty slots have a zero high word)
             sc = __uint_as_float((unsigned)(k >> 32));
             idx = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
             box = p.boxes[(size_t)b * p.tab.N + idx];
