@@ -24,8 +24,7 @@ struct AnchorGenParams {
 // reference evaluates them in Python double and stores to a float32 array).
 __global__ void __launch_bounds__(256)
 anchor_gen_kernel(const __grid_constant__ AnchorGenParams p, float4* __restrict__ dec,
-                  float4* __restrict__ enc, float4* __restrict__ cor, uint8_t* __restrict__ inside,
-                  float4* __restrict__ mcor) {
+                  float4* __restrict__ enc, float4* __restrict__ cor, uint8_t* __restrict__ inside) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.tab.N) return;
     int l = layer_of(p.tab, n);
@@ -53,14 +52,12 @@ anchor_gen_kernel(const __grid_constant__ AnchorGenParams p, float4* __restrict_
     if (p.has_border)
         in = (ymin >= p.lo_y[l]) && (xmin >= p.lo_x[l]) && (ymax < p.hi_y[l]) && (xmax < p.hi_x[l]);
     inside[n] = in ? 1 : 0;
-    mcor[n] = in ? make_float4(ymin, xmin, ymax, xmax)
-                 : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 }
 
 // Arbitrary flattened anchors: corners + inside mask from given (y, x, h, w) and per-anchor borders.
 __global__ void __launch_bounds__(256)
 anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ border, int N, int img_h, int img_w,
-                   float4* __restrict__ cor, uint8_t* __restrict__ inside, float4* __restrict__ mcor) {
+                   float4* __restrict__ cor, uint8_t* __restrict__ inside) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float4 a = yxhw[n];
@@ -74,8 +71,6 @@ anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ bord
         in = (ymin >= lo_y) && (xmin >= lo_x) && (ymax < hi_y) && (xmax < hi_x);
     }
     inside[n] = in ? 1 : 0;
-    mcor[n] = in ? make_float4(ymin, xmin, ymax, xmax)
-                 : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 }
 
 cudaError_t finish_compaction(ronk_anchors* h) {
@@ -183,14 +178,13 @@ extern "C" int ronk_anchors_create_flat(int img_h, int img_w, int N, const float
     if (e == cudaSuccess) e = cudaMalloc(&h->d_enc, (size_t)N * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cor, (size_t)N * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_inside, (size_t)N);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_mcor, (size_t)N * 16);
     if (e == cudaSuccess && border) e = cudaMalloc(&d_border, (size_t)N * 4);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_dec, yxhw, (size_t)N * 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_enc, yxhw, (size_t)N * 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && border) e = cudaMemcpy(d_border, border, (size_t)N * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         anchor_flat_kernel<<<(N + 255) / 256, 256>>>((const float4*)h->d_enc, d_border, N, img_h, img_w,
-                                                     (float4*)h->d_cor, h->d_inside, (float4*)h->d_mcor);
+                                                     (float4*)h->d_cor, h->d_inside);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
@@ -302,10 +296,9 @@ extern "C" int ronk_anchors_create(int kind, int img_h, int img_w, int num_layer
     if (e == cudaSuccess) e = cudaMalloc(&h->d_enc, (size_t)n * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_cor, (size_t)n * 16);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_inside, (size_t)n);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_mcor, (size_t)n * 16);
     if (e == cudaSuccess) {
         anchor_gen_kernel<<<(n + 255) / 256, 256>>>(*p, (float4*)h->d_dec, (float4*)h->d_enc,
-                                                    (float4*)h->d_cor, h->d_inside, (float4*)h->d_mcor);
+                                                    (float4*)h->d_cor, h->d_inside);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
@@ -327,7 +320,6 @@ extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
     if (h->d_enc) cudaFree(h->d_enc);
     if (h->d_cor) cudaFree(h->d_cor);
     if (h->d_inside) cudaFree(h->d_inside);
-    if (h->d_mcor) cudaFree(h->d_mcor);
     if (h->d_inside_idx) cudaFree(h->d_inside_idx);
     if (h->d_cidx) cudaFree(h->d_cidx);
     if (h->d_ccor) cudaFree(h->d_ccor);
