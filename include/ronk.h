@@ -198,6 +198,14 @@ int ronk_pairwise(const float* a, int G, const float* b, int N, int mode, float*
 int ronk_overlap_ref(const float* ref, int ref_n, const float* boxes, int N, int mode, float* out, void* stream);
 int ronk_select_mask(const float* pred, const float* boxes, int B, int n, int C, float select_threshold,
                      int ignore_class, float* out_scores, float* out_boxes, void* stream);
+/* mixed-class flavour:
+ * ronk_select_all_classes  tf_ssd_bboxes_select_layer_all_classes  nets/ssd_common.py:592-628
+ *                          pred [rows,C] -> classes int64 [rows], scores [rows]; use_threshold == 0 is the
+ *                          reference's "select_threshold is None or 0" branch
+ * ronk_gather_i64          the class gather of bboxes_sort_all_classes  tf_extended/bboxes.py:27-57 */
+int ronk_select_all_classes(const float* pred, long long rows, int C, int use_threshold, float threshold,
+                            int64_t* out_classes, float* out_scores, void* stream);
+int ronk_gather_i64(const int64_t* src, const int32_t* idx, int S, int N, int K, int64_t* out, void* stream);
 size_t ronk_dual_max_match_workspace_bytes(int G);
 int ronk_dual_max_match(const float* overlap, int G, int N, float high_thres, float low_thres, int match_flags,
                         int64_t* out_matched, float* out_scores, void* ws, void* stream);

@@ -50,6 +50,8 @@ SIGNATURES = {
     'ronk_overlap_ref': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'ronk_select_mask': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                  c_void_p]),
+    'ronk_select_all_classes': (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    'ronk_gather_i64': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ronk_dual_max_match_workspace_bytes': (c_size_t, [c_int]),
     'ronk_dual_max_match': (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),

@@ -521,3 +521,28 @@ def bboxes_resize(bbox_ref, boxes):
     with torch.cuda.device(b.device):
         _ffi.check(_ffi.lib().ronk_bboxes_resize(_ffi.farr(ref), _ptr(b), b.numel() // 4, _ptr(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- mixed-class flavour
+def select_all_classes(pred, select_threshold=None):
+    """pred [B,n,C] -> classes int64 [B,n], scores [B,n] (nets/ssd_common.py:592-628)."""
+    p = as_cuda(pred, torch.float32)
+    B, n, C = (int(v) for v in p.shape)
+    cls = torch.empty((B, n), dtype=torch.int64, device=p.device)
+    sc = torch.empty((B, n), dtype=torch.float32, device=p.device)
+    use = not (select_threshold is None or select_threshold == 0)
+    with torch.cuda.device(p.device):
+        _ffi.check(_ffi.lib().ronk_select_all_classes(_ptr(p), B * n, C, 1 if use else 0,
+                                                      float(select_threshold or 0.0), _ptr(cls), _ptr(sc), _stream()))
+    return cls, sc
+
+
+def gather_i64(src, idx):
+    """out[s, k] = src[s, idx[s, k]] (int64 rows, int32 indices)."""
+    src = as_cuda(src, torch.int64)
+    idx = as_cuda(idx, torch.int32, src.device)
+    S, N, K = int(src.shape[0]), int(src.shape[1]), int(idx.shape[1])
+    out = torch.empty((S, K), dtype=torch.int64, device=src.device)
+    with torch.cuda.device(src.device):
+        _ffi.check(_ffi.lib().ronk_gather_i64(_ptr(src), _ptr(idx), S, N, K, _ptr(out), _stream()))
+    return out

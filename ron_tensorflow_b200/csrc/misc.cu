@@ -67,6 +67,40 @@ select_mask_kernel(const float* __restrict__ pred, const float4* __restrict__ bo
     }
 }
 
+// tf_ssd_bboxes_select_layer_all_classes (ssd_common.py:592-628): one class + score per anchor.
+// use_thr == 0 (select_threshold None or 0): arg-max / max over ALL classes, score zeroed for class 0;
+// else: arg-max / max over classes 1.., class and score zeroed unless score > threshold.
+__global__ void __launch_bounds__(256)
+select_all_kernel(const float* __restrict__ pred, long long rows, int C, int use_thr, float thr,
+                  long long* __restrict__ out_cls, float* __restrict__ out_s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float* row = pred + i * C;
+    const int c0 = use_thr ? 1 : 0;
+    float best = row[c0];
+    int arg = c0;
+    for (int c = c0 + 1; c < C; ++c) {
+        const float v = row[c];
+        if (v > best) { best = v; arg = c; }      // tf.argmax: first occurrence
+    }
+    float m;
+    if (use_thr) m = (best > thr) ? 1.f : 0.f;    // :621-623
+    else m = (arg > 0) ? 1.f : 0.f;               // :616
+    out_cls[i] = use_thr ? (long long)arg * (long long)m : (long long)arg;
+    out_s[i] = best * m;
+}
+
+// out[s, k] = src[s, idx[s, k]] for int64 rows (bboxes_sort_all_classes, tf_extended/bboxes.py:44-54); idx < 0 -> 0
+__global__ void __launch_bounds__(256)
+gather_i64_kernel(const long long* __restrict__ src, const int* __restrict__ idx, int S, int N, int K,
+                  long long* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)S * K) return;
+    const long long srow = e / K;
+    const int j = idx[e];
+    out[e] = j >= 0 ? src[srow * N + j] : 0ll;
+}
+
 __device__ __forceinline__ unsigned ord_bits(float s) {
     unsigned u = __float_as_uint(s);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -179,6 +213,27 @@ extern "C" int ronk_select_mask(const float* pred, const float* boxes, int B, in
     long long tot = (long long)B * n;
     select_mask_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         pred, (const float4*)boxes, B, n, C, thr, ignore_class, out_scores, (float4*)out_boxes);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_select_all_classes(const float* pred, long long rows, int C, int use_threshold, float threshold,
+                                       int64_t* out_classes, float* out_scores, void* stream) {
+    RONK_REQUIRE(rows >= 0 && C >= 1 && (!use_threshold || C >= 2), RONK_EINVAL, "ronk_select_all_classes: bad sizes");
+    if (rows == 0) return RONK_OK;
+    RONK_REQUIRE(pred && out_classes && out_scores, RONK_EINVAL, "ronk_select_all_classes: NULL argument");
+    select_all_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        pred, rows, C, use_threshold ? 1 : 0, threshold, (long long*)out_classes, out_scores);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_gather_i64(const int64_t* src, const int32_t* idx, int S, int N, int K, int64_t* out, void* stream) {
+    RONK_REQUIRE(S >= 0 && N >= 0 && K >= 0, RONK_EINVAL, "ronk_gather_i64: bad sizes");
+    if ((long long)S * K == 0) return RONK_OK;
+    RONK_REQUIRE(src && idx && out, RONK_EINVAL, "ronk_gather_i64: NULL argument");
+    gather_i64_kernel<<<(unsigned)(((long long)S * K + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)src, idx, S, N, K, (long long*)out);
     RONK_LAUNCHED();
     return RONK_OK;
 }

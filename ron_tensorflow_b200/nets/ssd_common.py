@@ -185,3 +185,25 @@ def tf_ssd_bboxes_select(predictions_net, localizations_net, select_threshold=No
         d_s[c] = torch.cat([s[c] for s in l_s], dim=1)
         d_b[c] = torch.cat([b[c] for b in l_b], dim=1)
     return d_s, d_b
+
+
+def tf_ssd_bboxes_select_layer_all_classes(predictions_layer, localizations_layer, select_threshold=None):
+    """reference :592-628.  One class and score per anchor (mixed classes): classes int64 [B,n],
+    scores [B,n], boxes [B,n,4] (the localisations are assumed decoded, :626-627)."""
+    p = core.as_cuda(predictions_layer, torch.float32)
+    b = core.as_cuda(localizations_layer, torch.float32, p.device)
+    p = p.reshape(p.shape[0], -1, p.shape[-1])
+    b = b.reshape(b.shape[0], -1, b.shape[-1])
+    classes, scores = core.select_all_classes(p, select_threshold)
+    return classes, scores, b
+
+
+def tf_ssd_bboxes_select_all_classes(predictions_net, localizations_net, select_threshold=None, scope=None):
+    """reference :631-662: per-layer select, concatenated over layers on axis 1."""
+    l_c, l_s, l_b = [], [], []
+    for i in range(len(predictions_net)):
+        c, s, b = tf_ssd_bboxes_select_layer_all_classes(predictions_net[i], localizations_net[i], select_threshold)
+        l_c.append(c)
+        l_s.append(s)
+        l_b.append(b)
+    return torch.cat(l_c, dim=1), torch.cat(l_s, dim=1), torch.cat(l_b, dim=1)

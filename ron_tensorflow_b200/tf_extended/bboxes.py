@@ -2,7 +2,7 @@
 argument order, defaults, dict-keyed-by-class inputs/outputs; torch CUDA tensors replace TF
 tensors and every computation is a libronk kernel.
 
-reference map: bboxes_sort :60-101, bboxes_clip :105-144, bboxes_resize :147-171, bboxes_nms
+reference map: bboxes_sort_all_classes :27-57, bboxes_sort :60-101, bboxes_clip :105-144, bboxes_resize :147-171, bboxes_nms
 :173-234, bboxes_nms_batch :262-302, bboxes_matching :316-404, bboxes_matching_batch :407-450,
 bboxes_jaccard :527-554, bboxes_intersection :557-583.
 """
@@ -10,8 +10,15 @@ import torch
 
 from .. import core
 
-__all__ = ['bboxes_sort', 'bboxes_clip', 'bboxes_resize', 'bboxes_nms', 'bboxes_nms_batch', 'bboxes_matching',
+__all__ = ['bboxes_sort_all_classes', 'bboxes_sort', 'bboxes_clip', 'bboxes_resize', 'bboxes_nms', 'bboxes_nms_batch', 'bboxes_matching',
            'bboxes_matching_batch', 'bboxes_jaccard', 'bboxes_intersection']
+
+
+def bboxes_sort_all_classes(classes, scores, bboxes, top_k=400, scope=None):
+    """reference :27-57.  Mixed-class inputs: Batch x N classes / scores, Batch x N x 4 boxes ->
+    the top_k by decreasing score (ties: lower index first) with their classes and boxes."""
+    s, b, idx = core.sort_topk(scores, bboxes, top_k, want_idx=True)
+    return core.gather_i64(classes, idx), s, b
 
 
 def bboxes_sort(scores, bboxes, top_k=400, scope=None):

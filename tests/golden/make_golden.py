@@ -302,8 +302,32 @@ def gen_ron_eval():
     save('ron_eval', **out)
 
 
+# --------------------------------------------------------------------------- #
+# mixed-class select + sort (nets/ssd_common.py:592-662, tf_extended/bboxes.py:27-57)
+# --------------------------------------------------------------------------- #
+def gen_mixed():
+    out = {}
+    LS, FS = [250, 1000, 4000, 16000], [(5, 5), (10, 10), (20, 20), (40, 40)]
+    loc, pred, obj = synth.make_predictions(77, 1, 21250, 21, hot=300)
+    boxes = np.clip(loc * np.float32(0.1) + np.float32(0.5), 0, 1).astype(np.float32)   # any "decoded" boxes
+    P = [T(t) for t in synth.split_layers(pred, LS, FS, [10] * 4)]
+    Bx = [T(t) for t in synth.split_layers(boxes, LS, FS, [10] * 4)]
+    for tag, thr in (('none', None), ('thr', 0.05)):
+        c, s, b = ssd_common.tf_ssd_bboxes_select_all_classes(P, Bx, select_threshold=thr)
+        assert npy(c).dtype == np.int64 and np.array_equal(npy(b), boxes)
+        out[tag + '_classes'], out[tag + '_scores'] = npy(c).astype(np.uint8), npy(s)      # classes < 21: stored as bytes
+        c2, s2, b2 = tfe.bboxes.bboxes_sort_all_classes(c, s, b, top_k=300)
+        out[tag + '_sorted_classes'], out[tag + '_sorted_scores'], out[tag + '_sorted_boxes'] = npy(c2), npy(s2), npy(b2)
+    out['in_pred_sha'] = np.frombuffer(__import__('hashlib').sha256(pred.tobytes()).digest(), np.uint8)
+    save('mixed_select', **out)
+
+
 if __name__ == '__main__':
+    if '--only-mixed' in sys.argv:
+        gen_mixed()
+        sys.exit(0)
     gen_ron_eval()
+    gen_mixed()
     if '--only-ron-eval' in sys.argv:
         sys.exit(0)
     gen_anchors()
