@@ -546,3 +546,31 @@ def gather_i64(src, idx):
     with torch.cuda.device(src.device):
         _ffi.check(_ffi.lib().ronk_gather_i64(_ptr(src), _ptr(idx), S, N, K, _ptr(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- CUDA graphs
+class Graphed(object):
+    """Capture one call of ``fn(*args)`` (any function of this package: every libronk entry point is
+    asynchronous on the current stream and allocates nothing on the device itself) into a CUDA graph and
+    replay it: the 1-7 kernel launches of a step cost one graph launch.  ``args`` must be CUDA tensors
+    (or lists of them) that stay alive; refill them in place (``copy_``) before each ``replay()``.  The
+    outputs of the captured call are returned by ``replay()`` and are overwritten by the next replay.
+    Only for calls with static shapes (not the ``ron_eval`` functions, which read counts back)."""
+
+    def __init__(self, fn, *args, **kwargs):
+        _require_cuda()
+        self._args, self._kwargs = args, kwargs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm up: workspaces, function attributes, caches
+                fn(*args, **kwargs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*args, **kwargs)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

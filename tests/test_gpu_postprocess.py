@@ -344,3 +344,35 @@ def test_property_full_size_postprocess_batch256(ron, dec_anchors):
         eq(ni[b], o['idx'], 'kept anchor indices b=%d' % b)
         eq(ns[b], o['scores'], 'scores b=%d' % b)
         eq(nb[b], o['boxes'], 'boxes b=%d' % b)
+
+
+def test_cuda_graph_replay_matches_direct_calls(ron):
+    """core.Graphed: the post-process chain and the encode captured into CUDA graphs give the same
+    bits as direct calls, also after the inputs were refilled in place."""
+    import torch
+    from ron_tensorflow_b200 import core
+    net, anchors = ron
+    B = 4
+    ins = []
+    for seed in (11, 12):
+        loc, pred, obj = synth.make_predictions(seed, B, 21250, 21, hot=300)
+        ins.append([[torch.from_numpy(t).cuda() for t in _layers(x, False)] for x in (pred, loc, obj)])
+    st = [[t.clone() for t in part] for part in ins[0]]
+    fn = lambda p, l, o: net.detect(p, l, o, 0.03, 0.01, 0.45, [0., 0., 1., 1.], 400, 200)
+    g = core.Graphed(fn, st[0], st[1], st[2])
+    for k in (0, 1, 0):
+        for part, src in zip(st, ins[k]):
+            for d, s in zip(part, src):
+                d.copy_(s)
+        gs, gb = g.replay()
+        ds, db = fn(*ins[k])
+        assert torch.equal(gs, ds) and torch.equal(gb, db)
+    boxes, labels, counts = synth.make_gt_batch(2, 16, 1, 50)
+    d = [torch.from_numpy(x).cuda() for x in (boxes, labels, counts)]
+    ge = core.Graphed(lambda: core.match_encode(anchors.anchor_set, d[0], d[1], d[2], 0.56, 0.3))
+    r1 = ge.replay()
+    r2 = core.match_encode(anchors.anchor_set, d[0], d[1], d[2], 0.56, 0.3)
+    for k in ('labels', 'loc', 'scores'):
+        assert torch.equal(r1[k], r2[k])
+    r3 = ge.replay()
+    assert torch.equal(r3['labels'], r2['labels'])
