@@ -29,6 +29,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENC_B, ENC_G = 64, (1, 50)
+ENC_STREAMS, POST_STREAMS = 2, 3      # steps are issued round-robin on this many CUDA streams for `value`
 WORKLOAD = ('BASELINE configs[1]: RON-320 joint match+encode over all 4 layers (21250 anchors), batch 64 per GPU, '
             '1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels')
 POST_B, POST_K, POST_M, POST_THR = 256, 400, 200, 0.45
@@ -211,6 +212,36 @@ def timed_steps(torch, fn, steps, warmup, flush=None):
     return [a.elapsed_time(b) for a, b in evs]      # ms
 
 
+def pipelined_steps(torch, step, nstreams, steps, warmup):
+    """Whole-job time of `steps` back-to-back steps issued round-robin on `nstreams` CUDA streams
+    (step k runs on stream k % nstreams with that stream's own outputs / workspaces, so the tail of
+    one step overlaps the head of the next): W untimed warm-ups, then events on the current stream
+    around exactly `steps` steps, all streams joined before the end event.  Returns total ms."""
+    from ron_tensorflow_b200 import core
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+
+    def issue(k0, k1):
+        for s in streams:
+            s.wait_stream(main)
+        for k in range(k0, k1):
+            with torch.cuda.stream(streams[k % nstreams]):
+                step(k)
+        for s in streams:
+            main.wait_stream(s)
+
+    issue(0, max(warmup, nstreams))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = core.launch_count()
+    a.record(main)
+    issue(0, steps)
+    b.record(main)
+    torch.cuda.synchronize()
+    pipelined_steps.launches = core.launch_count() - l0
+    return a.elapsed_time(b)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -267,7 +298,19 @@ def run_ours(args):
     ms = timed_steps(torch, enc_step, args.steps, args.warmup, flush)
     enc_launches = timed_steps.launches
     barrier()
-    t_enc = max_over_ranks(sum(ms) / 1e3)
+    # whole-job throughput: the same steps issued round-robin on 2 streams (8 rotating output sets,
+    # 305 MB > L2, instead of the flush), so one step's drain overlaps the next step's ramp-up
+    outs_pipe = [new_out(ENC_B) for _ in range(8)]
+
+    def enc_pipe_step(k):
+        core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, out=outs_pipe[k % 8])
+
+    barrier()
+    ms_pipe = pipelined_steps(torch, enc_pipe_step, ENC_STREAMS, args.steps, args.warmup)
+    enc_launches = pipelined_steps.launches
+    barrier()
+    del outs_pipe
+    t_enc = max_over_ranks(ms_pipe / 1e3)
     enc_value = ENC_B * args.steps * world / t_enc
     enc_bytes = ENC_B * ENC_BYTES_PER_IMAGE + int(counts.sum()) * 24
     enc_achieved = enc_bytes / (np.mean(ms) * 1e-3) / 1e9
@@ -301,21 +344,27 @@ def run_ours(args):
     h_boxes = torch.from_numpy(boxes).pin_memory()
     h_labels = torch.from_numpy(labels).pin_memory()
     h_counts = torch.from_numpy(counts).pin_memory()
-    h_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+    # two streams, each with its own device inputs and pinned host outputs: the D2H of one step overlaps
+    # the H2D + kernel of the next (full-duplex PCIe)
+    E2E_STREAMS = 2
+    h_outs = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()} for _ in range(E2E_STREAMS)]
+    d_ins = [(torch.empty_like(d_boxes), torch.empty_like(d_labels), torch.empty_like(d_counts)) for _ in range(E2E_STREAMS)]
 
-    def enc_e2e_step():
-        d_boxes.copy_(h_boxes, non_blocking=True)
-        d_labels.copy_(h_labels, non_blocking=True)
-        d_counts.copy_(h_counts, non_blocking=True)
-        r = net.bboxes_encode_batch(d_labels, d_boxes, d_counts, anchors, 0.56, 0.3)
-        for k in h_out:
-            h_out[k].copy_(r[k], non_blocking=True)
+    def enc_e2e_step(k):
+        db, dl_, dc = d_ins[k % E2E_STREAMS]
+        db.copy_(h_boxes, non_blocking=True)
+        dl_.copy_(h_labels, non_blocking=True)
+        dc.copy_(h_counts, non_blocking=True)
+        r = net.bboxes_encode_batch(dl_, db, dc, anchors, 0.56, 0.3)
+        for name, h in h_outs[k % E2E_STREAMS].items():
+            h.copy_(r[name], non_blocking=True)
 
     barrier()
-    ms_e2e = timed_steps(torch, enc_e2e_step, args.steps, args.warmup)
+    ms_e2e = pipelined_steps(torch, enc_e2e_step, E2E_STREAMS, args.steps, args.warmup)
     barrier()
-    t_e2e = max_over_ranks(sum(ms_e2e) / 1e3)
+    t_e2e = max_over_ranks(ms_e2e / 1e3)
     enc_e2e = ENC_B * args.steps * world / t_e2e
+    h_out = h_outs[0]
     enc_h2d = boxes.nbytes + labels.nbytes + counts.nbytes
     enc_d2h = sum(v.numel() * v.element_size() for v in h_out.values())
 
@@ -344,25 +393,39 @@ def run_ours(args):
         ms_p = timed_steps(torch, post_step, args.steps, args.warmup)       # inputs (586 MB) exceed L2
         post_launches = timed_steps.launches
         barrier()
-        t_post = max_over_ranks(sum(ms_p) / 1e3)
+        def post_pipe_step(k):
+            ns, nb = net.detect(d_pred, d_loc, d_obj, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+            core.tpfp_match(ns, nb, d_gl, d_gb, d_gd, 0.5)
+
+        barrier()
+        ms_ppipe = pipelined_steps(torch, post_pipe_step, POST_STREAMS, args.steps, args.warmup)
+        post_launches = pipelined_steps.launches
+        barrier()
+        t_post = max_over_ranks(ms_ppipe / 1e3)
         post_value = POST_B * args.steps * world / t_post
         post_achieved = POST_B * POST_BYTES_PER_IMAGE / (np.mean(ms_p) * 1e-3) / 1e9
 
-        h_s = torch.empty((POST_B, N_CLASSES - 1, POST_M), dtype=torch.float32).pin_memory()
-        h_b = torch.empty((POST_B, N_CLASSES - 1, POST_M, 4), dtype=torch.float32).pin_memory()
+        h_ss = [torch.empty((POST_B, N_CLASSES - 1, POST_M), dtype=torch.float32).pin_memory() for _ in range(E2E_STREAMS)]
+        h_bs = [torch.empty((POST_B, N_CLASSES - 1, POST_M, 4), dtype=torch.float32).pin_memory() for _ in range(E2E_STREAMS)]
+        d_sets = [([torch.empty_like(t) for t in d_pred], [torch.empty_like(t) for t in d_loc], [torch.empty_like(t) for t in d_obj])
+                  for _ in range(E2E_STREAMS)]
 
-        def post_e2e_step():
-            for d, h in zip(d_loc + d_pred + d_obj, h_loc + h_pred + h_obj):
+        def post_e2e_step(k):
+            dp_, dl_, do_ = d_sets[k % E2E_STREAMS]
+            for d, h in zip(dl_ + dp_ + do_, h_loc + h_pred + h_obj):
                 d.copy_(h, non_blocking=True)
-            ns, nb = net.detect(d_pred, d_loc, d_obj, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
-            h_s.copy_(ns, non_blocking=True)
-            h_b.copy_(nb, non_blocking=True)
+            ns, nb = net.detect(dp_, dl_, do_, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+            h_ss[k % E2E_STREAMS].copy_(ns, non_blocking=True)
+            h_bs[k % E2E_STREAMS].copy_(nb, non_blocking=True)
 
+        n_pe = max(4, args.steps // 4)
         barrier()
-        ms_pe = timed_steps(torch, post_e2e_step, max(3, args.steps // 4), 3)
+        ms_pe = pipelined_steps(torch, post_e2e_step, E2E_STREAMS, n_pe, 3)
         barrier()
-        t_pe = max_over_ranks(sum(ms_pe) / 1e3)
-        post_e2e = POST_B * len(ms_pe) * world / t_pe
+        t_pe = max_over_ranks(ms_pe / 1e3)
+        post_e2e = POST_B * n_pe * world / t_pe
+        h_s, h_b = h_ss[0], h_bs[0]
+        del d_sets
 
         # VOC TP/FP records: accumulated on every rank, gathered ONCE with NCCL, AP on rank 0
         n_gt, tp, fp = res['tpfp']
@@ -381,10 +444,14 @@ def run_ours(args):
             aps.append(tfe.average_precision_voc07(p_, r_))
         post = {
             'metric': 'images/sec (decode+select+NMS)', 'value': post_value, 'unit': 'images/s',
-            'ms_per_step': float(np.mean(ms_p)),
+            'ms_per_step': ms_ppipe / args.steps,
+            'single_stream_ms_per_step': float(np.mean(ms_p)),
             'config': {'workload': 'BASELINE configs[2]: RON-320 eval post-process, batch %d per GPU, objectness 0.03, '
                                    'select 0.01, clip, min-size 0.03, top-k %d, NMS min-area %.2f keep %d, + VOC TP/FP kernel'
-                                   % (POST_B, POST_K, POST_THR, POST_M), 'l2': 'inputs (586 MB) exceed L2'},
+                                   % (POST_B, POST_K, POST_THR, POST_M), 'l2': 'inputs (586 MB) exceed L2',
+                       'pipelining': 'value / ms_per_step: steps round-robin on %d CUDA streams (own workspaces and outputs '
+                                     'each); roofline and single_stream_ms_per_step: one stream, events around each step'
+                                     % POST_STREAMS},
             'roofline': {'bound': 'hbm', 'achieved': post_achieved, 'peak': hbm, 'unit': 'GB/s',
                          'frac': post_achieved / hbm, 'traffic': traffic('postprocess_b256'), 'peak_source': peak_src,
                          'note': 'algorithmic 2.29 MB/image over the whole step (init, scatter x2, pivot, top-k, NMS, TP/FP: '
@@ -441,9 +508,14 @@ def run_ours(args):
     if rank == 0:
         line = {
             'metric': 'images/sec (match+encode)', 'value': enc_value, 'unit': 'images/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(ms)), 'higher_is_better': True,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_pipe / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'l2': 'flushed between timed steps (256 MB write)'},
+            'config': {'workload': WORKLOAD,
+                       'pipelining': 'value / ms_per_step: %d steps back to back, round-robin on %d CUDA streams, 8 rotating output '
+                                     'sets (305 MB > L2); roofline: the same step alone on one stream, CUDA events around each '
+                                     'launch, L2 flushed between steps (256 MB write): %.4f ms per step'
+                                     % (args.steps, ENC_STREAMS, float(np.mean(ms))),
+                       'l2': 'outputs rotate over 305 MB (> 126 MB L2) in the pipelined run; flushed in the single-stream run'},
             'roofline': {'bound': 'hbm', 'achieved': enc_achieved, 'peak': hbm, 'unit': 'GB/s',
                          'frac': enc_achieved / hbm, 'traffic': traffic('match_encode_b64'), 'peak_source': peak_src,
                          'note': 'algorithmic %d B/batch, one match_encode_kernel launch per step; the kernel is FP32-issue '
