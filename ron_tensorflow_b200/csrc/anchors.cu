@@ -107,6 +107,35 @@ cudaError_t finish_compaction(ronk_anchors* h) {
     if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_ccor, ccor.data(), ccor.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
 
+    // ---- post-process tile table (see common.cuh)
+    {
+        const LayerTable& t = h->tab;
+        std::vector<int> plain;
+        for (int l = 0; l < t.L; ++l) {
+            const int n_l = t.offs[l + 1] - t.offs[l];
+            for (int t0 = 0; t0 < n_l; t0 += kTileRows) {
+                const int rows = n_l - t0 < kTileRows ? n_l - t0 : kTileRows;
+                plain.insert(plain.end(), {l, t0, rows, n_l});
+            }
+        }
+        const int tpi = (int)(plain.size() / 4);
+        int m = (int)(0.618 * tpi);
+        auto gcd = [](int a, int b) { while (b) { int q = a % b; a = b; b = q; } return a; };
+        if (m < 1) m = 1;
+        while (m < tpi && gcd(m, tpi) != 1) ++m;
+        if (m >= tpi) m = 1;
+        std::vector<int> perm((size_t)tpi * 4);
+        for (int rp = 0; rp < tpi; ++rp) {
+            const int r = (int)(((long long)rp * m) % tpi);
+            for (int q = 0; q < 4; ++q) perm[(size_t)rp * 4 + q] = plain[(size_t)r * 4 + q];
+        }
+        h->tiles_per_image = tpi;
+        h->tile_perm_mul = m;
+        e = cudaMalloc(&h->d_tile_tab, perm.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_tile_tab, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
+
     // ---- work-item tables (see common.cuh).  A set of 64 consecutive inside anchors is "heavy" when its
     // bounding extent, clipped to the image, covers more than 40 % of it: then nearly every GT box
     // survives the cull and the item is as long as the GT list.
@@ -325,6 +354,7 @@ extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
     if (h->d_ccor) cudaFree(h->d_ccor);
     for (int t = 0; t < 3; ++t)
         if (h->d_items[t]) cudaFree(h->d_items[t]);
+    if (h->d_tile_tab) cudaFree(h->d_tile_tab);
     delete h;
 }
 

@@ -20,7 +20,6 @@
 
 namespace ronk {
 
-constexpr int kTileRows = 128;
 
 struct PostParams {
     LayerTable tab;
@@ -40,8 +39,9 @@ struct PostParams {
     int cap;
     long long num_tiles;
     // tile subset of this scatter launch: permuted tile index r' in [r_lo, r_hi) of every image,
-    // actual tile r = (r' * perm_mul) % tiles_per_image (perm_mul coprime: an even spread)
-    int r_lo, r_hi, perm_mul;
+    // (the handle's tile table is stored in that order: r' -> tile (r' * m) % tiles, m ~ 0.618 tiles, coprime)
+    int r_lo, r_hi;
+    const int4* tile_tab;            // [tiles per image] permuted tile table of the anchor handle
     int force_rebuild;               // test hook: always take the exact-rebuild path of pivoted segments
     int pivot_rank;                  // rank (from the top) of the sampled key that becomes the pivot; 0 = no sampling
     float* out_scores;
@@ -84,16 +84,15 @@ struct TileInfo {
     long long start_w, a0, a1, end_w;   // word offsets inside the layer's class array
 };
 
-// tile r of image b (r in [0, tiles per image))
-__device__ __forceinline__ TileInfo tile_info(const PostParams& p, int b, int r) {
+// tile rp (permuted index in [0, tiles per image)) of image b
+__device__ __forceinline__ TileInfo tile_info(const PostParams& p, int b, int rp) {
     TileInfo t;
+    const int4 e = __ldg(p.tile_tab + rp);
     t.b = b;
-    int l = 0;
-    while (l + 1 < p.tab.L && r >= p.tile_off[l + 1]) ++l;
-    t.layer = l;
-    t.n_l = p.tab.offs[l + 1] - p.tab.offs[l];
-    t.t0 = (r - p.tile_off[l]) * kTileRows;
-    t.rows = min(kTileRows, t.n_l - t.t0);
+    t.layer = e.x;
+    t.t0 = e.y;
+    t.rows = e.z;
+    t.n_l = e.w;
     t.start_w = ((long long)t.b * t.n_l + t.t0) * p.C;
     t.end_w = t.start_w + (long long)t.rows * p.C;
     long long total_w = (long long)p.B * t.n_l * p.C;
@@ -114,6 +113,40 @@ constexpr int kScatWarps = kTileRows / 32;
 // atomic per lane reserves the slots of all (up to 32) classes at once, pass 2 stores the u64 keys
 // (score bits << 32 | ~anchor).  TAIL: the last <= 3 score words of a layer array are not covered by
 // the 16-byte granular bulk copy and are read from global memory.
+// Fast form (every score word of the tile is in shared memory).  s_voff[j] = word offset of the j-th
+// surviving row inside the tile, or the offset of a row of -inf for a row whose box failed the size
+// test, so pass 1 is branch-free: one load of the (warp-uniform) offset, one of the score, a compare,
+// and a shift-in of the result bit.  Bit (nq - 1 - q) of `hit` belongs to the warp's q-th row.
+__device__ __forceinline__ void class_scan_fast(const PostParams& p, const TileInfo& t, const float* s_cls,
+                                                const int* s_voff, const int* s_vrow, int n_rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int CM = p.C - 1;
+    const unsigned nkey0 = 0xffffffffu - (unsigned)(p.tab.offs[t.layer] + t.t0);
+    const size_t seg0 = (size_t)t.b * CM;
+    const int nq = n_rows > warp ? (n_rows - warp + kScatWarps - 1) / kScatWarps : 0;
+    for (int cb = 0; cb < CM; cb += 32) {
+        const bool act = cb + lane < CM;
+        const int ci = act ? cb + lane : 0;
+        const float thr = act ? p.thr[seg0 + ci] : __int_as_float(0x7f800000);
+        const float* col = s_cls + 1 + ci;
+        unsigned hit = 0u;
+#pragma unroll 4
+        for (int j = warp; j < n_rows; j += kScatWarps) {
+            const float v = col[s_voff[j]];
+            hit = hit + hit + (v > thr ? 1u : 0u);
+        }
+        if (hit == 0u) continue;
+        u64* dst = p.keys + (seg0 + ci) * p.cap + atomicAdd(p.counts + seg0 + ci, __popc(hit));
+        while (hit) {
+            const int bp = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const int j = warp + (nq - 1 - bp) * kScatWarps;
+            const float v = col[s_voff[j]];
+            *dst++ = ((u64)__float_as_uint(v) << 32) | (u64)(nkey0 - (unsigned)s_vrow[j]);
+        }
+    }
+}
+
 template <bool TAIL>
 __device__ __forceinline__ void class_scan(const PostParams& p, const TileInfo& t, const float* s_cls,
                                            const int* s_vrows, int nslots) {
@@ -167,10 +200,12 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     const int C = p.C;
     const int stage_floats = (kTileRows * C + 4 + 3) & ~3;
     const int stage_bytes = stage_floats * 4 + kTileRows * 16;     // scores | loc rows
+    float* const s_ninf = reinterpret_cast<float*>(smem + 2 * (size_t)stage_bytes);   // C + 1 words of -inf
     __shared__ __align__(8) u64 s_bar[2];
     __shared__ int s_rows[kTileRows];
     __shared__ int s_wcnt[kScatWarps];
-    __shared__ int s_vrows[kTileRows];      // surviving rows with a valid box, compacted inside each 32-row chunk; -1 = empty
+    __shared__ int s_vrows[kTileRows];      // row of the j-th surviving anchor, -1 when its box failed the size test
+    __shared__ int s_voff[kTileRows];       // word offset of that row's scores inside the tile (or of the -inf row)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
@@ -179,6 +214,7 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         mbar_init(&s_bar[1], 1);
         fence_proxy_async();
     }
+    for (int i = tid; i <= C; i += kTileRows) s_ninf[i] = __int_as_float(0xff800000);
     __syncthreads();
 
     auto issue = [&](const TileInfo& t, int st) {
@@ -198,12 +234,11 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     };
 
     // tiles are visited grid-stride; (b, r) = (image, tile inside the image) advances without divisions
-    const int tpi = p.tile_off[p.tab.L];
     const int cnt = p.r_hi - p.r_lo;                    // tiles of this launch per image
     const int step_b = (int)(gridDim.x / (unsigned)cnt), step_r = (int)(gridDim.x % (unsigned)cnt);
     int b = (int)(blockIdx.x / (unsigned)cnt), r = (int)(blockIdx.x % (unsigned)cnt);
     if (b >= p.B) return;
-    TileInfo t = tile_info(p, b, (int)(((unsigned)(p.r_lo + r) * (unsigned)p.perm_mul) % (unsigned)tpi));
+    TileInfo t = tile_info(p, b, p.r_lo + r);
     if (tid == 0) issue(t, 0);
     bool gate = load_gate(t);
     unsigned phase = 0u;   // bit st = parity the next wait on stage st must see
@@ -215,7 +250,7 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         TileInfo tn = t;
         bool gate_next = false;
         if (nb < p.B) {
-            tn = tile_info(p, nb, (int)(((unsigned)(p.r_lo + nr) * (unsigned)p.perm_mul) % (unsigned)tpi));
+            tn = tile_info(p, nb, p.r_lo + nr);
             if (tid == 0) issue(tn, st ^ 1);
             gate_next = load_gate(tn);          // objectness of the next tile: the load overlaps this tile's work
         }
@@ -260,18 +295,18 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
                 const float qn = __int_as_float(0x7fc00000);
                 p.boxes[(size_t)t.b * p.tab.N + n] = valid ? box : make_float4(qn, qn, qn, qn);
             }
-            const unsigned vm = __ballot_sync(full, valid);
-            s_vrows[tid] = -1;
-            __syncwarp();
-            if (valid) s_vrows[warp * 32 + __popc(vm & ((1u << lane) - 1u))] = rr;
+            if (tid < n_gated) {
+                s_vrows[tid] = valid ? rr : -1;
+                s_voff[tid] = valid ? rr * C : (int)(s_ninf - s_cls);
+            }
         }
         __syncthreads();
 
-        // ---- C. class scan over the surviving valid rows
+        // ---- C. class scan over the surviving rows
         if (t.end_w > t.a1)
-            class_scan<true>(p, t, s_cls, s_vrows, nchunks * 32);
+            class_scan<true>(p, t, s_cls, s_vrows, n_gated);
         else
-            class_scan<false>(p, t, s_cls, s_vrows, nchunks * 32);
+            class_scan_fast(p, t, s_cls, s_voff, s_vrows, n_gated);
         __syncthreads();   // stage st, s_rows and s_vrows are free again
         t = tn;
         b = nb;
@@ -844,7 +879,7 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     RONK_LAUNCHED();
 
     const int stage_floats = (kTileRows * C + 4 + 3) & ~3;
-    size_t smem_a = (size_t)2 * ((size_t)stage_floats * 4 + kTileRows * 16);
+    size_t smem_a = (size_t)2 * ((size_t)stage_floats * 4 + kTileRows * 16) + (size_t)(C + 1 + 3) / 4 * 16;
     RONK_REQUIRE(smem_a <= 220 * 1024, RONK_ELIMIT, "ronk_decode_select_topk: C too large for the shared-memory tile");
     if (smem_a > 48 * 1024)
         RONK_CUDA(cudaFuncSetAttribute(scatter_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
@@ -854,20 +889,16 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     // Two scatter launches when the lists would be much longer than K: first a spread-out sixteenth of
     // every image's tiles (threshold sel_thr), then a per-(image, class) pivot from those keys,
     // then all other tiles with the pivot as threshold.  perm_mul ~ 0.618 * tiles, coprime.
-    const int tpi = toff;
+    const int tpi = h->tiles_per_image;        // == toff; the handle's tile table is in the permuted order
+    const int m = h->tile_perm_mul;
+    p.tile_tab = (const int4*)h->d_tile_tab;
     int tpi1 = 0;
-    p.perm_mul = 1;
     p.pivot_rank = 0;
     p.force_rebuild = (select_flags & RONK_SELECT_TEST_REBUILD) ? 1 : 0;
     if (!(select_flags & RONK_SELECT_NO_SAMPLING) && tpi >= 16 && (long long)K * 8 <= h->tab.N) {
         tpi1 = tpi / 16;                 // a sixteenth of the tiles: pivot rank mu + 4 sigma + 8 still leaves ~2K keys per list
         if (tpi1 < 2) tpi1 = 2;
         if (tpi1 > 16) tpi1 = 16;
-        int m = (int)(0.618 * tpi);
-        auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-        while (m < tpi && gcd(m, tpi) != 1) ++m;
-        if (m >= tpi) m = 1;
-        p.perm_mul = m;
         long long rows = 0;
         for (int q = 0; q < tpi1; ++q) {
             int r = (int)(((long long)q * m) % tpi);
