@@ -48,5 +48,5 @@ dg = [torch.from_numpy(x).cuda() for x in (gl, gb, gl * 0)]
 def post(k):
     ns, nb = net.detect(dp, dl, do, 0.03, 0.01, 0.45, [0., 0., 1., 1.], 400, 200)
     core.tpfp_match(ns, nb, dg[0], dg[1], dg[2], 0.5)
-for ns in (1, 2, 3):
+for ns in (1, 2, 3, 4, 6):
     print('post B=256   streams=%d  %.1f us/step' % (ns, run(post, ns, steps=24, warm=4)))
