@@ -235,6 +235,27 @@ int ronk_gather_rows(const void* src, int row_bytes, const int32_t* idx, int m, 
 int ronk_bboxes_resize(const float* bbox_ref_host /*[4]*/, const float* boxes, long long n, float* out_boxes,
                        void* stream);
 
+/* per-class NMS variants of ron_eval.py (the heavy steps are ronk_sort_topk + ronk_nms_batch):
+ * ronk_class_columns   tf_bboxes_nms_by_class  ron_eval.py:212-232   scores [n,C], boxes [n,4] -> one segment per class:
+ *                      col_scores [C,n], col_boxes [C,n,4]; entries that do not start alive (score <= threshold, :228)
+ *                      are zeroed, so they sort last and never suppress or get suppressed
+ * ronk_keep_by_class   ron_eval.py:263-264,276-288   kept_pos / kept_scores [C,M] (positions in each class's sorted
+ *                      list, -1 = padding), sorted_idx [C,n] -> max / first arg-max over classes of scores * keep_mask,
+ *                      out_mask = max > 0; keep_ws is n*C bytes of scratch
+ * ronk_group_by_label  tf_bboxes_nms_by_class_v1  ron_eval.py:338-345   sorted labels / scores / boxes -> segment c-1 holds,
+ *                      in order, the entries with label c (c = 1..num_classes-1), zero padded to n; seg_pos = their
+ *                      positions in the sorted list (-1 = padding)
+ * ronk_mark_positions  ron_eval.py:344   OR of the per-class keep masks: out_mask[seg_pos[s, kept[s,m]]] = 1 */
+int ronk_class_columns(const float* scores, const float* boxes, int n, int C, float threshold,
+                       float* col_scores, float* col_boxes, void* stream);
+int ronk_keep_by_class(const float* scores, int n, int C, const int32_t* kept_pos, const float* kept_scores, int M,
+                       const int32_t* sorted_idx, float threshold, uint8_t* keep_ws, float* out_max,
+                       int64_t* out_labels, uint8_t* out_mask, void* stream);
+int ronk_group_by_label(const int64_t* labels, const float* scores, const float* boxes, int n, int num_classes,
+                        float* seg_scores, float* seg_boxes, int32_t* seg_pos, void* stream);
+int ronk_mark_positions(const int32_t* kept, const int32_t* seg_pos, int S, int M, int n, uint8_t* out_mask,
+                        void* stream);
+
 /* number of kernel launches issued by this library in this process since load
  * (bench.py reports it as gpu_launches) */
 long long ronk_launch_count(void);

@@ -64,6 +64,11 @@ SIGNATURES = {
     'ronk_compact_indices': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ronk_gather_rows': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'ronk_bboxes_resize': (c_int, [P(c_float), c_void_p, c_longlong, c_void_p, c_void_p]),
+    'ronk_class_columns': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    'ronk_keep_by_class': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ronk_group_by_label': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ronk_mark_positions': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ronk_tpfp_match': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -523,6 +523,59 @@ def bboxes_resize(bbox_ref, boxes):
     return out
 
 
+def class_columns(scores, boxes, threshold):
+    """scores [n,C], boxes [n,4] -> col_scores [C,n], col_boxes [C,n,4] (ronk_class_columns)."""
+    s = as_cuda(scores, torch.float32)
+    b = as_cuda(boxes, torch.float32, s.device).reshape(-1, 4)
+    n, C = int(s.shape[0]), int(s.shape[1])
+    cs = torch.empty((C, n), dtype=torch.float32, device=s.device)
+    cb = torch.empty((C, n, 4), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        _ffi.check(_ffi.lib().ronk_class_columns(_ptr(s), _ptr(b), n, C, float(threshold), _ptr(cs), _ptr(cb), _stream()))
+    return cs, cb
+
+
+def keep_by_class(scores, kept_pos, kept_scores, sorted_idx, threshold):
+    """ron_eval.py:263-264,276-288 -> (max [n], labels int64 [n], mask uint8 [n]) (ronk_keep_by_class)."""
+    s = as_cuda(scores, torch.float32)
+    n, C = int(s.shape[0]), int(s.shape[1])
+    M = int(kept_pos.shape[1])
+    ws = torch.empty((n * C,), dtype=torch.uint8, device=s.device)
+    mx = torch.empty((n,), dtype=torch.float32, device=s.device)
+    lab = torch.empty((n,), dtype=torch.int64, device=s.device)
+    mask = torch.empty((n,), dtype=torch.uint8, device=s.device)
+    with torch.cuda.device(s.device):
+        _ffi.check(_ffi.lib().ronk_keep_by_class(_ptr(s), n, C, _ptr(kept_pos.contiguous()), _ptr(kept_scores.contiguous()), M,
+                                                 _ptr(sorted_idx.contiguous()), float(threshold), _ptr(ws), _ptr(mx),
+                                                 _ptr(lab), _ptr(mask), _stream()))
+    return mx, lab, mask
+
+
+def group_by_label(labels, scores, boxes, num_classes):
+    """Sorted labels [n] / scores [n] / boxes [n,4] -> per-class segments [C-1,n] (ronk_group_by_label)."""
+    l = as_cuda(labels, torch.int64)
+    s = as_cuda(scores, torch.float32, l.device)
+    b = as_cuda(boxes, torch.float32, l.device).reshape(-1, 4)
+    n, S = int(l.shape[0]), int(num_classes) - 1
+    ss = torch.empty((S, n), dtype=torch.float32, device=l.device)
+    sb = torch.empty((S, n, 4), dtype=torch.float32, device=l.device)
+    sp = torch.empty((S, n), dtype=torch.int32, device=l.device)
+    with torch.cuda.device(l.device):
+        _ffi.check(_ffi.lib().ronk_group_by_label(_ptr(l), _ptr(s), _ptr(b), n, int(num_classes), _ptr(ss), _ptr(sb),
+                                                  _ptr(sp), _stream()))
+    return ss, sb, sp
+
+
+def mark_positions(kept, seg_pos):
+    """mask uint8 [n]: OR over segments of the kept entries' positions (ronk_mark_positions)."""
+    S, M, n = int(kept.shape[0]), int(kept.shape[1]), int(seg_pos.shape[1])
+    mask = torch.empty((n,), dtype=torch.uint8, device=kept.device)
+    with torch.cuda.device(kept.device):
+        _ffi.check(_ffi.lib().ronk_mark_positions(_ptr(kept.contiguous()), _ptr(seg_pos.contiguous()), S, M, n, _ptr(mask),
+                                                  _stream()))
+    return mask
+
+
 # ----------------------------------------------------------------------------- mixed-class flavour
 def select_all_classes(pred, select_threshold=None):
     """pred [B,n,C] -> classes int64 [B,n], scores [B,n] (nets/ssd_common.py:592-628)."""

@@ -163,6 +163,105 @@ resize_kernel(const float4* __restrict__ in, long long n, float4 v, float4 s, fl
     out[i] = b;
 }
 
+
+// ---- per-class NMS variants of ron_eval.py (tf_bboxes_nms_by_class :212-291, _v1 :293-366)
+
+// by_class front end: column c of scores [n,C] becomes segment c; entries that do not start alive
+// (score <= select_threshold, :228) become zero score / zero box, which sort after every live entry
+// and never take part in a suppression (zero volume -> safe_divide gives 0).
+__global__ void __launch_bounds__(256)
+class_columns_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes, int n, int C, float thr,
+                     float* __restrict__ col_scores, float4* __restrict__ col_boxes) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n * C) return;
+    const int c = (int)(e / n), i = (int)(e - (long long)c * n);
+    const float v = scores[(size_t)i * C + c];
+    const bool live = v > thr;
+    col_scores[e] = live ? v : 0.f;
+    col_boxes[e] = live ? boxes[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// keep_mask[orig, c] = 1 for every entry the NMS of class c kept (:263-264); kept_pos are positions
+// in the sorted list of the class (-1 padding), sorted_idx maps them back to the rows.
+__global__ void __launch_bounds__(256)
+mark_kept_kernel(const int* __restrict__ kept_pos, const float* __restrict__ kept_scores,
+                 const int* __restrict__ sorted_idx, int C, int M, int n, float thr, uint8_t* __restrict__ keep) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= C * M) return;
+    const int c = e / M, pos = kept_pos[e];
+    if (pos < 0 || !(kept_scores[e] > thr)) return;
+    keep[(size_t)sorted_idx[(size_t)c * n + pos] * C + c] = 1;
+}
+
+// :282-288: keep_scores = scores * mask, its max / first arg-max over classes, keep = max > 0
+__global__ void __launch_bounds__(256)
+keep_reduce_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ keep, int n, int C,
+                   float* __restrict__ out_max, long long* __restrict__ out_label, uint8_t* __restrict__ out_mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float best = 0.f;
+    int label = 0;
+    for (int c = 0; c < C; ++c) {
+        const float v = scores[(size_t)i * C + c] * (keep[(size_t)i * C + c] ? 1.f : 0.f);
+        if (c == 0 || v > best) { best = v; label = c; }
+    }
+    out_max[i] = best;
+    out_label[i] = label;
+    out_mask[i] = best > 0.f ? 1 : 0;
+}
+
+// _v1 front end: one CTA per class c = blockIdx.x + 1 gathers, in order, the entries of the sorted
+// list whose label is c (:340) into segment blockIdx.x; the rest of the segment is zero padding.
+__global__ void __launch_bounds__(256)
+group_by_label_kernel(const long long* __restrict__ labels, const float* __restrict__ scores,
+                      const float4* __restrict__ boxes, int n, float* __restrict__ seg_scores,
+                      float4* __restrict__ seg_boxes, int* __restrict__ seg_pos) {
+    __shared__ int s_w[8];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long cls = (long long)blockIdx.x + 1;
+    const size_t base = (size_t)blockIdx.x * n;
+    int pos = 0;
+    for (int k0 = 0; k0 < n; k0 += 256) {
+        const int i = k0 + threadIdx.x;
+        const bool mine = i < n && labels[i] == cls;
+        const unsigned m = __ballot_sync(full, mine);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            before += (w < warp) ? s_w[w] : 0;
+            all += s_w[w];
+        }
+        if (mine) {
+            const int o = pos + before + __popc(m & ((1u << lane) - 1u));
+            seg_scores[base + o] = scores[i];
+            seg_boxes[base + o] = boxes[i];
+            seg_pos[base + o] = i;
+        }
+        pos += all;
+    }
+    for (int o = pos + threadIdx.x; o < n; o += 256) {
+        seg_scores[base + o] = 0.f;
+        seg_boxes[base + o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        seg_pos[base + o] = -1;
+    }
+}
+
+// _v1: total_keep_mask |= keep_mask of the class (:344); kept are positions inside the segment
+__global__ void __launch_bounds__(256)
+mark_positions_kernel(const int* __restrict__ kept, const int* __restrict__ seg_pos, int S, int M, int n,
+                      uint8_t* __restrict__ mask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S * M) return;
+    const int k = kept[e];
+    if (k < 0) return;
+    const int i = seg_pos[(size_t)(e / M) * n + k];
+    if (i >= 0) mask[i] = 1;
+}
+
 }  // namespace ronk
 
 using namespace ronk;
@@ -269,6 +368,59 @@ extern "C" int ronk_bboxes_resize(const float* bbox_ref, const float* boxes, lon
     resize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, n, v,
                                                                               make_float4(sh, sw, sh, sw),
                                                                               (float4*)out_boxes);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_class_columns(const float* scores, const float* boxes, int n, int C, float threshold,
+                                  float* col_scores, float* col_boxes, void* stream) {
+    RONK_REQUIRE(n >= 0 && C >= 1 && (n == 0 || (scores && boxes && col_scores && col_boxes)), RONK_EINVAL,
+                 "ronk_class_columns: bad argument");
+    if (n == 0) return RONK_OK;
+    RONK_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)col_boxes % 16) == 0, RONK_EINVAL,
+                 "ronk_class_columns: box pointers must be 16-byte aligned");
+    const long long total = (long long)n * C;
+    class_columns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        scores, (const float4*)boxes, n, C, threshold, col_scores, (float4*)col_boxes);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_keep_by_class(const float* scores, int n, int C, const int32_t* kept_pos, const float* kept_scores,
+                                  int M, const int32_t* sorted_idx, float threshold, uint8_t* keep_ws, float* out_max,
+                                  int64_t* out_labels, uint8_t* out_mask, void* stream) {
+    RONK_REQUIRE(n >= 1 && C >= 1 && M >= 1 && scores && kept_pos && kept_scores && sorted_idx && keep_ws && out_max &&
+                     out_labels && out_mask,
+                 RONK_EINVAL, "ronk_keep_by_class: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    RONK_CUDA(cudaMemsetAsync(keep_ws, 0, (size_t)n * C, st));
+    mark_kept_kernel<<<(unsigned)((C * M + 255) / 256), 256, 0, st>>>(kept_pos, kept_scores, sorted_idx, C, M, n, threshold,
+                                                                  keep_ws);
+    RONK_LAUNCHED();
+    keep_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scores, keep_ws, n, C, out_max, (long long*)out_labels,
+                                                                 out_mask);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_group_by_label(const int64_t* labels, const float* scores, const float* boxes, int n,
+                                   int num_classes, float* seg_scores, float* seg_boxes, int32_t* seg_pos, void* stream) {
+    RONK_REQUIRE(n >= 1 && num_classes >= 2 && labels && scores && boxes && seg_scores && seg_boxes && seg_pos, RONK_EINVAL,
+                 "ronk_group_by_label: bad argument");
+    RONK_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)seg_boxes % 16) == 0, RONK_EINVAL,
+                 "ronk_group_by_label: box pointers must be 16-byte aligned");
+    group_by_label_kernel<<<(unsigned)(num_classes - 1), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)labels, scores, (const float4*)boxes, n, seg_scores, (float4*)seg_boxes, seg_pos);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_mark_positions(const int32_t* kept, const int32_t* seg_pos, int S, int M, int n, uint8_t* out_mask,
+                                   void* stream) {
+    RONK_REQUIRE(S >= 1 && M >= 1 && n >= 1 && kept && seg_pos && out_mask, RONK_EINVAL, "ronk_mark_positions: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    RONK_CUDA(cudaMemsetAsync(out_mask, 0, (size_t)n, st));
+    mark_positions_kernel<<<(unsigned)((S * M + 255) / 256), 256, 0, st>>>(kept, seg_pos, S, M, n, out_mask);
     RONK_LAUNCHED();
     return RONK_OK;
 }

@@ -1,6 +1,7 @@
 """Drop-in for the post-process functions of the reference's ``ron_eval.py`` (single-image
 evaluation): ``flaten_predict`` :111-144, ``filter_boxes`` :369-392,
-the class-agnostic ``tf_bboxes_nms`` :146-210 -- same names, argument order and defaults.  The
+the class-agnostic ``tf_bboxes_nms`` :146-210 and the per-class ``tf_bboxes_nms_by_class`` :212-291 /
+``tf_bboxes_nms_by_class_v1`` :293-366 -- same names, argument order and defaults.  The
 thresholds the reference reads from ``tf.app.flags.FLAGS`` live in the module-level ``FLAGS``
 object below (same names and defaults, ron_eval.py:82-91).
 
@@ -19,6 +20,7 @@ class _Flags(object):
     objectness_thres = 0.95      # :86-87
     nms_topk_percls = 10         # :88-89
     nms_topk = 20                # :90-91
+    num_classes = 21             # :61-62
 
 
 FLAGS = _Flags()
@@ -69,3 +71,49 @@ def tf_bboxes_nms(scores, labels, bboxes, nms_threshold=0.5, keep_top_k=200, mod
     pos = core.gather_rows(ni[0].contiguous(), kept)                # positions in the sorted list
     src = core.gather_rows(si[0].contiguous(), pos)                 # positions before sorting
     return core.gather_rows(ns[0].contiguous(), kept), core.gather_rows(labels, src), core.gather_rows(nb[0].contiguous(), kept)
+
+
+def tf_bboxes_nms_by_class(scores, labels, bboxes, nms_threshold=0.5, keep_top_k=200, mode='min', scope=None):
+    """reference ron_eval.py:212-291: one greedy NMS per class column over the boxes whose score in that
+    column exceeds FLAGS.select_threshold (at most keep_top_k picks each); a box survives with the best of
+    the scores it was kept for and that class as its new label.  scores [n,C]; returns (score [k], label
+    int64 [k], box [k,4]) in the input order."""
+    if mode not in ('union', 'min'):
+        raise ValueError('unknown mode to use for nms.')
+    if FLAGS.select_threshold < 0:
+        raise ValueError('tf_bboxes_nms_by_class: a negative select_threshold is not supported')
+    s = core.as_cuda(scores, torch.float32)
+    b = core.as_cuda(bboxes, torch.float32, s.device).reshape(-1, 4)
+    n = int(s.shape[0])
+    if n < 1:                                                                       # tf.cond(num_anchors < 1, ...) :291
+        return s, core.as_cuda(labels, torch.int64, s.device), b
+    cs, cb = core.class_columns(s, b, FLAGS.select_threshold)                      # :228 + the transpose of :277
+    ss, sb, si = core.sort_topk(cs, cb, n, want_idx=True)                          # :217-218
+    ns, _, ni = core.nms_batch(ss, sb, nms_threshold, keep_top_k, mode, assume_sorted=True, want_idx=True)
+    mx, lab, mask = core.keep_by_class(s, ni, ns, si, FLAGS.select_threshold)      # :263-264,282-288
+    idx = core.compact_indices(mask)
+    return core.gather_rows(mx, idx), core.gather_rows(lab, idx), core.gather_rows(b, idx)
+
+
+def tf_bboxes_nms_by_class_v1(scores, labels, bboxes, nms_threshold=0.5, keep_top_k=200, mode='min', scope=None):
+    """reference ron_eval.py:293-366: boxes above FLAGS.select_threshold (best class score) are sorted once;
+    for every class 1..FLAGS.num_classes-1 a greedy NMS runs among the boxes carrying that label (at most
+    keep_top_k picks each); the union of the survivors, cut to the first keep_top_k, is returned in
+    decreasing score order."""
+    if mode not in ('union', 'min'):
+        raise ValueError('unknown mode to use for nms.')
+    s = core.as_cuda(scores, torch.float32)
+    best, mask = core.rowmax_mask(s, FLAGS.select_threshold)                      # :295-296
+    idx = core.compact_indices(mask)
+    best = core.gather_rows(best, idx)
+    labels = core.gather_rows(core.as_cuda(labels, torch.int64, s.device), idx)
+    bboxes = core.gather_rows(core.as_cuda(bboxes, torch.float32, s.device).reshape(-1, 4), idx)
+    n = int(best.shape[0])
+    if n < 1:                                                                       # :366
+        return best, labels, bboxes
+    ss, sb, si = core.sort_topk(best.reshape(1, n), bboxes.reshape(1, n, 4), n, want_idx=True)    # :301-302
+    sl = core.gather_rows(labels, si[0].contiguous())
+    gs, gb, gp = core.group_by_label(sl, ss[0], sb[0], FLAGS.num_classes)          # nms_mask = (labels == cls) :340
+    _, _, ni = core.nms_batch(gs, gb, nms_threshold, keep_top_k, mode, assume_sorted=True, want_idx=True)
+    kept = core.compact_indices(core.mark_positions(ni, gp))[:keep_top_k]           # :344, :349-352
+    return core.gather_rows(ss[0].contiguous(), kept), core.gather_rows(sl, kept), core.gather_rows(sb[0].contiguous(), kept)

@@ -270,11 +270,11 @@ def gen_tpfp():
 def gen_ron_eval():
     import ast
     src = open(os.path.join(REF, 'ron_eval.py')).read()
-    want = {'flaten_predict', 'tf_bboxes_nms', 'filter_boxes'}
+    want = {'flaten_predict', 'tf_bboxes_nms', 'filter_boxes', 'tf_bboxes_nms_by_class', 'tf_bboxes_nms_by_class_v1'}
     body = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want]
 
     class F(object):
-        select_threshold, nms_threshold, objectness_thres, nms_topk = 0.02, 0.4, 0.03, 20
+        select_threshold, nms_threshold, objectness_thres, nms_topk, num_classes = 0.02, 0.4, 0.03, 20, 21
     ns = {'tf': tf, 'tfe': tfe, 'np': np, 'FLAGS': F}
     exec(compile(ast.Module(body=body, type_ignores=[]), 'ron_eval.py', 'exec'), ns)
     out = {}
@@ -293,6 +293,12 @@ def gen_ron_eval():
         b = tfe.bboxes.bboxes_clip(T(bbox_img), b)
         s, l, b = ns['filter_boxes'](s, l, b, 0.03, T(np.array(img, np.int32)), [320., 320.])
         out[tag + '_filt_scores'], out[tag + '_filt_labels'], out[tag + '_filt_boxes'] = npy(s), npy(l), npy(b)
+        # the two per-class variants (ron_eval.py:212-366) on the same filtered boxes; keep_top_k 10 / 12
+        # so that both the per-class cap and the final cut of _v1 (:361-363) are exercised
+        cs, cl, cb = ns['tf_bboxes_nms_by_class'](s, l, b, nms_threshold=F.nms_threshold, keep_top_k=10, mode=mode)
+        out[tag + '_bycls_scores'], out[tag + '_bycls_labels'], out[tag + '_bycls_boxes'] = npy(cs), npy(cl), npy(cb)
+        cs, cl, cb = ns['tf_bboxes_nms_by_class_v1'](s, l, b, nms_threshold=F.nms_threshold, keep_top_k=12, mode=mode)
+        out[tag + '_v1_scores'], out[tag + '_v1_labels'], out[tag + '_v1_boxes'] = npy(cs), npy(cl), npy(cb)
         s, l, b = ns['tf_bboxes_nms'](s, l, b, nms_threshold=F.nms_threshold, keep_top_k=keep, mode=mode)
         out[tag + '_nms_scores'], out[tag + '_nms_labels'], out[tag + '_nms_boxes'] = npy(s), npy(l), npy(b)
         ref = np.array([0.1, 0.05, 0.9, 0.95], np.float32)

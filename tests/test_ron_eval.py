@@ -1,5 +1,6 @@
 """ron_eval.py single-image post-process variant: flaten_predict ->
-clip -> filter_boxes -> class-agnostic tf_bboxes_nms -> bboxes_resize.  The golden fixture was made
+clip -> filter_boxes -> class-agnostic tf_bboxes_nms (or the per-class tf_bboxes_nms_by_class / _v1) ->
+bboxes_resize.  The golden fixture was made
 by the reference's own function source executed over the TF-1 shim (tests/golden/make_golden.py)."""
 import hashlib
 
@@ -35,6 +36,12 @@ def test_oracle_matches_reference_functions(golden, tag):
     b = O.clip_boxes([0., 0., 1., 1.], b)
     s, l, b = O.filter_boxes(s, l, b, 0.03, img, [320., 320.])
     assert np.array_equal(s, g[tag + '_filt_scores']) and np.array_equal(b, g[tag + '_filt_boxes'])
+    cs, cl, cb = O.bboxes_nms_by_class(s, l, b, SEL, NMS, 10, mode)
+    assert np.array_equal(cs, g[tag + '_bycls_scores']) and np.array_equal(cl, g[tag + '_bycls_labels'])
+    assert np.array_equal(cb, g[tag + '_bycls_boxes'])
+    cs, cl, cb = O.bboxes_nms_by_class_v1(s, l, b, SEL, 21, NMS, 12, mode)
+    assert np.array_equal(cs, g[tag + '_v1_scores']) and np.array_equal(cl, g[tag + '_v1_labels'])
+    assert np.array_equal(cb, g[tag + '_v1_boxes'])
     s, l, b = O.bboxes_nms_agnostic(s, l, b, SEL, NMS, keep, mode)
     assert np.array_equal(s, g[tag + '_nms_scores']) and np.array_equal(l, g[tag + '_nms_labels'])
     assert np.array_equal(b, g[tag + '_nms_boxes'])
@@ -62,6 +69,10 @@ def test_cuda_matches_reference_functions(golden, tag):
     b = tfe.bboxes_clip([0., 0., 1., 1.], b)
     s, l, b = ron_eval.filter_boxes(s, l, b, 0.03, img, [320., 320.])
     eq(s, g[tag + '_filt_scores'], 'filtered scores'); eq(l, g[tag + '_filt_labels'], 'filtered labels'); eq(b, g[tag + '_filt_boxes'], 'filtered boxes')
+    cs, cl, cb = ron_eval.tf_bboxes_nms_by_class(s, l, b, nms_threshold=NMS, keep_top_k=10, mode=mode)
+    eq(cs, g[tag + '_bycls_scores'], 'by-class scores'); eq(cl, g[tag + '_bycls_labels'], 'by-class labels'); eq(cb, g[tag + '_bycls_boxes'], 'by-class boxes')
+    cs, cl, cb = ron_eval.tf_bboxes_nms_by_class_v1(s, l, b, nms_threshold=NMS, keep_top_k=12, mode=mode)
+    eq(cs, g[tag + '_v1_scores'], 'v1 scores'); eq(cl, g[tag + '_v1_labels'], 'v1 labels'); eq(cb, g[tag + '_v1_boxes'], 'v1 boxes')
     s, l, b = ron_eval.tf_bboxes_nms(s, l, b, nms_threshold=NMS, keep_top_k=keep, mode=mode)
     eq(s, g[tag + '_nms_scores'], 'nms scores'); eq(l, g[tag + '_nms_labels'], 'nms labels'); eq(b, g[tag + '_nms_boxes'], 'nms boxes')
     eq(tfe.bboxes_resize([0.1, 0.05, 0.9, 0.95], b), g[tag + '_resized'], 'resized')
@@ -86,6 +97,13 @@ def test_cuda_vs_oracle_dense_and_empty():
     os_, ol, ob = O.flaten_predict([pred[0]], [obj[0]], [boxes], 0.03)
     assert os_.shape[0] > 5000
     eq(s, os_, 'scores'); eq(l, ol, 'labels'); eq(b, ob, 'boxes')
+    for mode, keep in (('min', 40), ('union', 7)):               # per-class variants on the ~8k dense boxes
+        cs, cl, cb = ron_eval.tf_bboxes_nms_by_class(s, l, b, nms_threshold=0.45, keep_top_k=keep, mode=mode)
+        rs, rl, rb = O.bboxes_nms_by_class(os_, ol, ob, 0.002, 0.45, keep, mode)
+        eq(cs, rs, 'by-class scores'); eq(cl, rl, 'by-class labels'); eq(cb, rb, 'by-class boxes')
+        cs, cl, cb = ron_eval.tf_bboxes_nms_by_class_v1(s, l, b, nms_threshold=0.45, keep_top_k=keep, mode=mode)
+        rs, rl, rb = O.bboxes_nms_by_class_v1(os_, ol, ob, 0.002, 21, 0.45, keep, mode)
+        eq(cs, rs, 'v1 scores'); eq(cl, rl, 'v1 labels'); eq(cb, rb, 'v1 boxes')
     s, l, b = ron_eval.tf_bboxes_nms(s, l, b, nms_threshold=0.45, keep_top_k=300, mode='union')
     os_, ol, ob = O.bboxes_nms_agnostic(os_, ol, ob, 0.002, 0.45, 300, 'union')
     eq(s, os_, 'nms scores'); eq(l, ol, 'nms labels'); eq(b, ob, 'nms boxes')
@@ -93,5 +111,8 @@ def test_cuda_vs_oracle_dense_and_empty():
     s, l, b = ron_eval.flaten_predict(P, Ob, [torch.from_numpy(t) for t in Bx])
     assert s.shape == (0, 21) and l.shape == (0,) and b.shape == (0, 4)
     s, l, b = ron_eval.filter_boxes(s, l, b, 0.03, (375, 500), [320., 320.])
-    s, l, b = ron_eval.tf_bboxes_nms(s, l, b)
-    assert s.shape == (0,) and l.shape == (0,) and b.shape == (0, 4)
+    for fn in (ron_eval.tf_bboxes_nms_by_class_v1, ron_eval.tf_bboxes_nms):
+        rs, rl, rb = fn(s, l, b)
+        assert rs.shape == (0,) and rl.shape == (0,) and rb.shape == (0, 4)
+    rs, rl, rb = ron_eval.tf_bboxes_nms_by_class(s, l, b)      # n < 1: the inputs come back unchanged (:291)
+    assert rs.shape == (0, 21) and rl.shape == (0,) and rb.shape == (0, 4)
