@@ -491,6 +491,36 @@ def run_ours(args):
                    'config': {'workload': 'decode -> flaten_predict -> clip -> filter_boxes -> class-agnostic NMS (union, '
                                           'keep 20) -> resize, one RON-320 image per step; shapes are data dependent, so '
                                           'the chain reads 4 counts back to the host (latency bound)'}}
+
+    # ---------------------------------------------------------------- next row: RON loss example masks
+    lossmask = None
+    if not args.no_postprocess:
+        from ron_tensorflow_b200.nets import ron_vgg_320 as rv
+        nl = ENC_B * N
+        rngl = np.random.Generator(np.random.PCG64(4242 + rank))
+        d_gc = torch.from_numpy(rngl.choice(np.array([-1, 0, 0, 0, 0, 0, 0, 0, 3, 17], np.int64), size=nl)).to(dev)
+        d_ob = torch.from_numpy(rngl.random(nl, dtype=np.float32)).to(dev)
+        d_r1 = torch.from_numpy(rngl.random(nl, dtype=np.float32)).to(dev)
+        d_r2 = torch.from_numpy(rngl.random(nl, dtype=np.float32)).to(dev)
+        d_lc = torch.from_numpy(rngl.normal(0, 1, (nl, 4)).astype(np.float32)).to(dev)
+        d_gl = torch.from_numpy(rngl.normal(0, 1, (nl, 4)).astype(np.float32)).to(dev)
+
+        def lossmask_step():
+            m_ = rv.ron_loss_masks(d_gc, d_ob, d_r1, d_r2, objness_threshold=0.03, negative_ratio=3.)
+            return rv.ron_localization_loss(d_lc, d_gl, m_['cls_positive_mask'])
+
+        barrier()
+        ms_l = timed_steps(torch, lossmask_step, args.steps, args.warmup, flush=flush)
+        barrier()
+        # algorithmic bytes per anchor: masks read 8 + 4 + 4 + 4 and write 1 + 4 + 1 + 1; the localisation term reads
+        # 1 mask byte and 2 x 16 B of boxes for the class positives only (counted for every anchor: upper bound 59 B)
+        lm_bytes = nl * 27.0 + nl * 1.0
+        lossmask = {'metric': 'images/sec (RON loss example masks + localisation term)', 'value': world * ENC_B * 1e3 / float(np.mean(ms_l)),
+                    'unit': 'images/s', 'ms_per_step': float(np.mean(ms_l)), 'gpu_launches': timed_steps.launches,
+                    'roofline': {'bound': 'hbm', 'achieved': lm_bytes / (float(np.mean(ms_l)) * 1e-3) / 1e9, 'peak': hbm,
+                                 'unit': 'GB/s', 'frac': lm_bytes / (float(np.mean(ms_l)) * 1e-3) / 1e9 / hbm, 'traffic': None},
+                    'config': {'workload': 'ron_losses masks (ron_vgg_320.py:686-740) + localisation loss (:760-764) on the '
+                                           'targets of one batch of %d RON-320 images; uniforms are inputs; L2 flushed' % ENC_B}}
     clocks = sampler.stop()
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
@@ -526,7 +556,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(enc_d2h)},
             'gpu_launches': int(enc_launches),
             'clocks': clocks,
-            'stages': {'encode_b256': enc256, 'postprocess': post, 'ron_eval_single_image': roneval},
+            'stages': {'encode_b256': enc256, 'postprocess': post, 'ron_eval_single_image': roneval, 'loss_masks_b64': lossmask},
         }
         print_line(json.dumps(line))
     if world > 1:

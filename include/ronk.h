@@ -256,6 +256,27 @@ int ronk_group_by_label(const int64_t* labels, const float* scores, const float*
 int ronk_mark_positions(const int32_t* kept, const int32_t* seg_pos, int S, int M, int n, uint8_t* out_mask,
                         void* stream);
 
+/* ------------------------------------------- RON loss example masks + smooth-L1
+ * (the consumer of the encode outputs)
+ * ronk_loss_masks         ron_losses  nets/ron_vgg_320.py:686-740   flat gclasses int64 [n], objectness scores [n] and
+ *                         the two tf.random_uniform draws [n] (:705,:738; inputs, so results are reproducible) ->
+ *                         final_neg_mask_objness u8 [n] (:707), objness_pred_label i32 [n] (:710),
+ *                         cls_positive_mask u8 [n] (:726), final_cls_neg_mask_objness u8 [n] (:740),
+ *                         counts f32 [4] or NULL = n_positives, n_negtives, n_cls_positives, n_cls_negtives.
+ *                         n < 2^24 (the reference counts with float32 sums).  ws: ronk_loss_workspace_bytes()
+ * ronk_smooth_l1          modified_smooth_l1  nets/custom_layers.py:31-50   element-wise, scalar weights
+ * ronk_localization_loss  nets/ron_vgg_320.py:760-764   beta * mean over cls_positive of the row sums of
+ *                         modified_smooth_l1(sigma); 0 without positives.  Accumulates in double */
+size_t ronk_loss_workspace_bytes(void);
+int ronk_loss_masks(const int64_t* gclasses, const float* objness_pred, const float* rand_objness,
+                    const float* rand_cls, long long n, float objness_threshold, float negative_ratio,
+                    uint8_t* out_final_objness, int32_t* out_objness_label, uint8_t* out_cls_positive,
+                    uint8_t* out_final_cls, float* out_counts, void* ws, void* stream);
+int ronk_smooth_l1(const float* pred, const float* target, long long count, float inside_weight,
+                   float outside_weight, double sigma, float* out, void* stream);
+int ronk_localization_loss(const float* localisations, const float* glocalisations, const uint8_t* cls_positive,
+                           long long n, double sigma, float beta, float* out_loss, void* ws, void* stream);
+
 /* number of kernel launches issued by this library in this process since load
  * (bench.py reports it as gpu_launches) */
 long long ronk_launch_count(void);

@@ -592,8 +592,54 @@ device = _Scope
 control_dependencies = _Scope
 
 
+# hooks for the golden generator: ron_losses (nets/ron_vgg_320.py:635-771) returns nothing, so the masks it
+# wraps in tf.stop_gradient and the losses it hands to tf.losses.add_loss are recorded here; the uniforms
+# of tf.random_uniform come from ``_rng`` (set by the caller) and are recorded too.
+_stop_gradient_log = []
+_loss_log = []
+_random_log = []
+_rng = None
+
+
 def stop_gradient(x, name=None):
+    _stop_gradient_log.append(x)
     return x
+
+
+def random_uniform(shape, minval=0, maxval=None, dtype=None, seed=None, name=None):
+    if _rng is None:
+        raise RuntimeError('tf-shim: set tensorflow._rng = numpy.random.Generator(...) before tf.random_uniform')
+    shp = _shape_arg(shape)
+    u = _rng.random(size=shp, dtype=np.float32)
+    hi = np.float32(1.0 if maxval is None else maxval)
+    lo = np.float32(minval)
+    u = (u * (hi - lo) + lo).astype(np.float32)
+    _random_log.append(u)
+    return Tensor(u)
+
+
+def abs(x, name=None):
+    return Tensor(np.abs(_v(x)))
+
+
+def reduce_mean(x, axis=None, keep_dims=False, name=None, keepdims=None):
+    a = _v(x)
+    # float64 accumulate, one rounding: the reduction ORDER of the real kernel is unspecified,
+    # so means are compared with a tolerance, never bit for bit
+    r = np.mean(a.astype(np.float64), axis=_axis(axis), keepdims=_pybool(keep_dims or keepdims))
+    return Tensor(np.asarray(r).astype(a.dtype))
+
+
+def _sparse_softmax_xent(_sentinel=None, labels=None, logits=None, name=None):
+    z = _v(logits).astype(np.float64)
+    l = _v(labels).astype(np.int64)
+    m = z.max(-1, keepdims=True)
+    lse = np.log(np.exp(z - m).sum(-1)) + m[..., 0]
+    return Tensor((lse - np.take_along_axis(z, l[..., None], -1)[..., 0]).astype(np.float32))
+
+
+def _add_loss(loss, loss_collection=None):
+    _loss_log.append(loss)
 
 
 def identity(x, name=None):
@@ -690,6 +736,9 @@ if not any(isinstance(f, _Finder) for f in sys.meta_path):
 
 nn = _StubModule('tensorflow.nn')
 nn.top_k = _top_k
+nn.sparse_softmax_cross_entropy_with_logits = _sparse_softmax_xent
+losses = _StubModule('tensorflow.losses')
+losses.add_loss = _add_loss
 contrib = _Stub('tensorflow.contrib')
 app = _Stub('tensorflow.app')
 logging = _Stub('tensorflow.logging')

@@ -601,6 +601,63 @@ def gather_i64(src, idx):
     return out
 
 
+# ----------------------------------------------------------------------------- RON loss masks
+def loss_masks(gclasses, objness_pred, rand_objness, rand_cls, objness_threshold=0.03, negative_ratio=3.):
+    """nets/ron_vgg_320.py:686-740 on flat tensors (any common shape; flattened in C order).  Returns
+    (final_neg_mask_objness, objness_pred_label int32, cls_positive_mask, final_cls_neg_mask_objness, counts f32[4]);
+    masks are torch.bool."""
+    g = as_cuda(gclasses, torch.int64)
+    dev, shape = g.device, tuple(g.shape)
+    o = as_cuda(objness_pred, torch.float32, dev)
+    r1 = as_cuda(rand_objness, torch.float32, dev)
+    r2 = as_cuda(rand_cls, torch.float32, dev)
+    n = g.numel()
+    if not (o.numel() == n and r1.numel() == n and r2.numel() == n):
+        raise ValueError('gclasses, objness_pred and the two random draws must have the same number of elements')
+    fo = torch.empty(shape, dtype=torch.uint8, device=dev)
+    lab = torch.empty(shape, dtype=torch.int32, device=dev)
+    cp = torch.empty(shape, dtype=torch.uint8, device=dev)
+    fc = torch.empty(shape, dtype=torch.uint8, device=dev)
+    cnt = torch.empty((4,), dtype=torch.float32, device=dev)
+    L = _ffi.lib()
+    ws = _workspace('loss', L.ronk_loss_workspace_bytes(), False, dev)
+    with torch.cuda.device(dev):
+        _ffi.check(L.ronk_loss_masks(_ptr(g), _ptr(o), _ptr(r1), _ptr(r2), n, float(objness_threshold), float(negative_ratio),
+                                     _ptr(fo), _ptr(lab), _ptr(cp), _ptr(fc), _ptr(cnt), _ptr(ws), _stream()))
+    return fo.view(torch.bool), lab, cp.view(torch.bool), fc.view(torch.bool), cnt
+
+
+def smooth_l1(bbox_pred, bbox_targets, inside_weight=1., outside_weight=1., sigma=1.):
+    """nets/custom_layers.py:31-50, element-wise."""
+    a = as_cuda(bbox_pred, torch.float32)
+    b = as_cuda(bbox_targets, torch.float32, a.device)
+    if a.shape != b.shape:
+        raise ValueError('bbox_pred and bbox_targets must have the same shape')
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _ffi.check(_ffi.lib().ronk_smooth_l1(_ptr(a), _ptr(b), a.numel(), float(inside_weight), float(outside_weight),
+                                             float(sigma), _ptr(out), _stream()))
+    return out
+
+
+def localization_loss(localisations, glocalisations, cls_positive_mask, sigma=3., beta=1. / 3):
+    """nets/ron_vgg_320.py:760-764 -> float32 scalar tensor on the device."""
+    a = as_cuda(localisations, torch.float32).reshape(-1, 4)
+    b = as_cuda(glocalisations, torch.float32, a.device).reshape(-1, 4)
+    m = cls_positive_mask
+    m = (m.view(torch.uint8) if isinstance(m, torch.Tensor) and m.dtype == torch.bool else as_cuda(m, torch.uint8, a.device))
+    m = m.to(a.device).reshape(-1).contiguous()
+    if not (a.shape == b.shape and m.numel() == a.shape[0]):
+        raise ValueError('localisations / glocalisations [n,4] and cls_positive_mask [n] expected')
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    L = _ffi.lib()
+    ws = _workspace('loss', L.ronk_loss_workspace_bytes(), False, a.device)
+    with torch.cuda.device(a.device):
+        _ffi.check(L.ronk_localization_loss(_ptr(a), _ptr(b), _ptr(m), int(a.shape[0]), float(sigma), float(beta), _ptr(out),
+                                            _ptr(ws), _stream()))
+    return out[0]
+
+
 # ----------------------------------------------------------------------------- CUDA graphs
 class Graphed(object):
     """Capture one call of ``fn(*args)`` (any function of this package: every libronk entry point is

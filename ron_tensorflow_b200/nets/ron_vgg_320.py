@@ -2,7 +2,9 @@
 ``RONParams``, ``RONNet.{anchors, bboxes_encode, bboxes_decode, bboxes_filter_min,
 detected_bboxes}``, ``ron_anchor_one_layer``, ``ron_anchors_all_layers`` -- same names,
 argument order, defaults and return structure, with torch CUDA tensors where the reference
-has TF tensors.  The network definition and the loss (reference :361-778) are out of scope.
+has TF tensors.  The network definition (reference :361-630) is out of scope; of the loss
+(:635-771) the example masks and the localisation term are provided (``ron_loss_masks``,
+``ron_localization_loss``: SURVEY.md section 8f rank 2), the two cross-entropy terms stay with the network.
 
 Additions (never replacements): ``RONNet.bboxes_encode_batch`` (padded batch of images,
 optional matched indices / objectness labels) and ``RONNet.detect`` (fused decode +
@@ -190,3 +192,41 @@ def _nms_to_dicts(s, b, nms_threshold, keep_top_k, mode='min'):
                                assume_sorted=True)
     ns, nb = ns.view(B, CM, -1), nb.view(B, CM, -1, 4)
     return {c + 1: ns[:, c] for c in range(CM)}, {c + 1: nb[:, c] for c in range(CM)}
+
+
+# =========================================================================== #
+# RON loss: example masks + localisation term (reference :635-771)
+# =========================================================================== #
+def ron_loss_masks(gclasses, objness_pred, rand_objness=None, rand_cls=None, objness_threshold=0.03,
+                   negative_ratio=3., generator=None):
+    """reference nets/ron_vgg_320.py:686-740.  ``gclasses`` / ``objness_pred``: the encode labels and the
+    objectness scores, flat or lists over layers (flattened and concatenated like :660-675).  The two
+    ``tf.random_uniform`` draws of the reference (:705, :738) are ``rand_objness`` / ``rand_cls``; when
+    omitted they are drawn on the device (``generator``: optional torch.Generator).
+    Returns a dict: ``final_neg_mask_objness``, ``objness_pred_label`` (int32), ``cls_positive_mask``,
+    ``final_cls_neg_mask_objness`` (bool tensors) and ``counts`` = float32 [n_positives, n_negtives,
+    n_cls_positives, n_cls_negtives]."""
+    def flat(x, dtype):
+        if isinstance(x, (list, tuple)):
+            return torch.cat([core.as_cuda(t, dtype).reshape(-1) for t in x], 0)
+        return core.as_cuda(x, dtype).reshape(-1)
+    g = flat(gclasses, torch.int64)
+    o = flat(objness_pred, torch.float32)
+    if rand_objness is None:
+        rand_objness = torch.rand(g.shape, device=g.device, dtype=torch.float32, generator=generator)
+    if rand_cls is None:
+        rand_cls = torch.rand(g.shape, device=g.device, dtype=torch.float32, generator=generator)
+    fo, lab, cp, fc, cnt = core.loss_masks(g, o, flat(rand_objness, torch.float32), flat(rand_cls, torch.float32),
+                                           objness_threshold, negative_ratio)
+    return dict(final_neg_mask_objness=fo, objness_pred_label=lab, cls_positive_mask=cp,
+                final_cls_neg_mask_objness=fc, counts=cnt)
+
+
+def ron_localization_loss(localisations, glocalisations, cls_positive_mask, beta=1. / 3, sigma=3.):
+    """reference nets/ron_vgg_320.py:760-764: beta * mean over the class positives of the row sums of
+    modified_smooth_l1(localisations, glocalisations, sigma=3); 0 when there is no class positive."""
+    def flat(x):
+        if isinstance(x, (list, tuple)):
+            return torch.cat([core.as_cuda(t, torch.float32).reshape(-1, 4) for t in x], 0)
+        return core.as_cuda(x, torch.float32).reshape(-1, 4)
+    return core.localization_loss(flat(localisations), flat(glocalisations), cls_positive_mask, sigma, beta)

@@ -91,3 +91,14 @@ def split_layers(x, layer_sizes, feat_shapes=None, anchors_per_cell=None):
         out.append(t)
         o += n
     return out
+
+
+def make_loss_inputs(seed, batch, num_anchors=21250, num_classes=21):
+    """Synthetic network outputs for the loss-mask stage (reference nets/ron_vgg_320.py:635-771): class logits
+    [B,N,C], localisations [B,N,4], objectness logits [B,N,2] and objectness scores [B,N] = sigmoid(N(-3,2))."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    logits = rng.normal(0, 1, (batch, num_anchors, num_classes)).astype(np.float32)
+    loc = rng.normal(0, 0.5, (batch, num_anchors, 4)).astype(np.float32)
+    obj_logits = rng.normal(0, 1, (batch, num_anchors, 2)).astype(np.float32)
+    obj_pred = (1. / (1. + np.exp(-rng.normal(-3, 2, (batch, num_anchors))))).astype(np.float32)
+    return logits, loc, obj_logits, obj_pred

@@ -328,7 +328,68 @@ def gen_mixed():
     save('mixed_select', **out)
 
 
+# --------------------------------------------------------------------------- #
+# RON loss masks + smooth-L1 (nets/ron_vgg_320.py:635-771, nets/custom_layers.py:31-50)
+# --------------------------------------------------------------------------- #
+def gen_loss_masks():
+    from nets import custom_layers
+    out = {}
+    FS = [(5, 5), (10, 10), (20, 20), (40, 40)]
+    LS = [250, 1000, 4000, 16000]
+    net = ron_vgg_320.RONNet()
+    anchors = net.anchors(net.params.img_shape)
+    for tag, seed, batch, g_lo, g_hi in (('a', 501, 2, 3, 12), ('b', 502, 1, 1, 1)):
+        logits, loc, obj_logits, obj_pred = synth.make_loss_inputs(seed, batch)
+        gb, gl, gc = synth.make_gt_batch(7, batch, g_lo, g_hi, first_image=seed)
+        cls_l, loc_l, sc_l = [[] for _ in LS], [[] for _ in LS], [[] for _ in LS]
+        for b in range(batch):
+            c, l, s_, _ = net.bboxes_encode(T(gl[b, :gc[b]]), T(gb[b, :gc[b]]), anchors, positive_threshold=0.56, ignore_threshold=0.3)
+            for i in range(len(LS)):
+                cls_l[i].append(npy(c[i]).reshape(FS[i] + (10,)))
+                loc_l[i].append(npy(l[i]))
+                sc_l[i].append(npy(s_[i]).reshape(FS[i] + (10,)))
+        gcls = [np.stack(v) for v in cls_l]
+        gloc = [np.stack(v) for v in loc_l]
+        gsc = [np.stack(v) for v in sc_l]
+        split = lambda x, ch: [T(t) for t in synth.split_layers(x, LS, FS, [10] * 4)] if ch else None
+        tf._rng = np.random.Generator(np.random.PCG64(seed + 1))
+        del tf._stop_gradient_log[:], tf._loss_log[:], tf._random_log[:]
+        ron_vgg_320.ron_losses([T(t) for t in synth.split_layers(logits, LS, FS, [10] * 4)],
+                               [T(t) for t in synth.split_layers(loc, LS, FS, [10] * 4)],
+                               [T(t) for t in synth.split_layers(obj_logits, LS, FS, [10] * 4)],
+                               [T(t) for t in synth.split_layers(obj_pred[..., None], LS, FS, [10] * 4)],
+                               [T(t) for t in gcls], [T(t) for t in gloc], [T(t) for t in gsc],
+                               objness_threshold=0.03, negative_ratio=3.)
+        sg = [npy(t) for t in tf._stop_gradient_log]
+        # order of the tf.stop_gradient calls in ron_losses: final_neg_mask_objness :707, objness_pred_label :710,
+        # cls_positive_mask :726, final_cls_neg_mask_objness :740, clipped gclasses :751, glocalisations :760,
+        # cls_positive_mask again :764
+        assert len(sg) == 7 and sg[0].dtype == bool and sg[1].dtype == np.int32 and sg[2].dtype == bool and sg[3].dtype == bool
+        assert len(tf._random_log) == 2 and len(tf._loss_log) == 3
+        out[tag + '_final_neg_mask_objness'] = np.packbits(sg[0])
+        out[tag + '_objness_pred_label'] = np.packbits(sg[1].astype(bool))
+        out[tag + '_cls_positive_mask'] = np.packbits(sg[2])
+        out[tag + '_final_cls_neg_mask_objness'] = np.packbits(sg[3])
+        out[tag + '_losses'] = np.array([float(npy(v)) for v in tf._loss_log], np.float32)     # cls, objectness, localisation
+        # flat (layer-major) inputs of the mask stage, as ron_losses sees them (:660-675)
+        flat = lambda ls: np.concatenate([np.asarray(t).reshape(-1) for t in ls])
+        out[tag + '_gclasses'] = flat(gcls).astype(np.int8)
+        out[tag + '_rand_sha'] = np.frombuffer(__import__('hashlib').sha256(tf._random_log[0].tobytes() + tf._random_log[1].tobytes()).digest(), np.uint8)
+        out[tag + '_cfg'] = np.array([seed, batch, g_lo, g_hi], np.int64)
+        # element-wise smooth-L1 of the first 64 rows of the flat order (bit-exact check)
+        fl = np.concatenate([t.reshape(-1, 4) for t in synth.split_layers(loc, LS, FS, [10] * 4)])
+        fg = np.concatenate([t.reshape(-1, 4) for t in gloc])
+        pick = np.nonzero(flat(gcls) > 0)[0][:64]
+        out[tag + '_sl1_pred'], out[tag + '_sl1_target'] = fl[pick], fg[pick]
+        out[tag + '_sl1'] = npy(custom_layers.modified_smooth_l1(T(fl[pick]), T(fg[pick]), sigma=3.))
+        out[tag + '_sl1_w'] = npy(custom_layers.modified_smooth_l1(T(fl[pick]), T(fg[pick]), 0.5, 2., sigma=1.))
+    save('loss_masks', **out)
+
+
 if __name__ == '__main__':
+    if '--only-loss' in sys.argv:
+        gen_loss_masks()
+        sys.exit(0)
     if '--only-mixed' in sys.argv:
         gen_mixed()
         sys.exit(0)
@@ -341,3 +402,4 @@ if __name__ == '__main__':
     gen_postprocess()
     gen_nms()
     gen_tpfp()
+    gen_loss_masks()
