@@ -263,15 +263,21 @@ int ronk_mark_positions(const int32_t* kept, const int32_t* seg_pos, int S, int 
  *                         final_neg_mask_objness u8 [n] (:707), objness_pred_label i32 [n] (:710),
  *                         cls_positive_mask u8 [n] (:726), final_cls_neg_mask_objness u8 [n] (:740),
  *                         counts f32 [4] or NULL = n_positives, n_negtives, n_cls_positives, n_cls_negtives.
- *                         n < 2^24 (the reference counts with float32 sums).  ws: ronk_loss_workspace_bytes()
+ *                         n < 2^24 (the reference counts with float32 sums).  With localisations / glocalisations
+ *                         [n,4] (or both NULL) the same launch also produces out_loss[0] = the localisation term below.
+ *                         ws: ronk_loss_workspace_bytes(), zeroed once with ronk_loss_workspace_init; every call
+ *                         leaves it zeroed again.  One cooperative launch
  * ronk_smooth_l1          modified_smooth_l1  nets/custom_layers.py:31-50   element-wise, scalar weights
  * ronk_localization_loss  nets/ron_vgg_320.py:760-764   beta * mean over cls_positive of the row sums of
  *                         modified_smooth_l1(sigma); 0 without positives.  Accumulates in double */
 size_t ronk_loss_workspace_bytes(void);
+int ronk_loss_workspace_init(void* ws, void* stream);
 int ronk_loss_masks(const int64_t* gclasses, const float* objness_pred, const float* rand_objness,
                     const float* rand_cls, long long n, float objness_threshold, float negative_ratio,
                     uint8_t* out_final_objness, int32_t* out_objness_label, uint8_t* out_cls_positive,
-                    uint8_t* out_final_cls, float* out_counts, void* ws, void* stream);
+                    uint8_t* out_final_cls, float* out_counts, const float* localisations,
+                    const float* glocalisations, double sigma, float beta, float* out_loss, void* ws,
+                    void* stream);
 int ronk_smooth_l1(const float* pred, const float* target, long long count, float inside_weight,
                    float outside_weight, double sigma, float* out, void* stream);
 int ronk_localization_loss(const float* localisations, const float* glocalisations, const uint8_t* cls_positive,

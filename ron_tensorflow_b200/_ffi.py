@@ -70,8 +70,10 @@ SIGNATURES = {
     'ronk_group_by_label': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ronk_mark_positions': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ronk_loss_workspace_bytes': (c_size_t, []),
+    'ronk_loss_workspace_init': (c_int, [c_void_p, c_void_p]),
     'ronk_loss_masks': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_void_p, c_void_p,
+                                c_void_p]),
     'ronk_smooth_l1': (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_float, c_double, c_void_p, c_void_p]),
     'ronk_localization_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_float, c_void_p, c_void_p,
                                        c_void_p]),

@@ -602,10 +602,12 @@ def gather_i64(src, idx):
 
 
 # ----------------------------------------------------------------------------- RON loss masks
-def loss_masks(gclasses, objness_pred, rand_objness, rand_cls, objness_threshold=0.03, negative_ratio=3.):
-    """nets/ron_vgg_320.py:686-740 on flat tensors (any common shape; flattened in C order).  Returns
-    (final_neg_mask_objness, objness_pred_label int32, cls_positive_mask, final_cls_neg_mask_objness, counts f32[4]);
-    masks are torch.bool."""
+def loss_masks(gclasses, objness_pred, rand_objness, rand_cls, objness_threshold=0.03, negative_ratio=3.,
+               localisations=None, glocalisations=None, sigma=3., beta=1. / 3):
+    """nets/ron_vgg_320.py:686-740 on flat tensors (any common shape; flattened in C order), one launch.
+    Returns (final_neg_mask_objness, objness_pred_label int32, cls_positive_mask, final_cls_neg_mask_objness,
+    counts f32[4], loss); masks are torch.bool; ``loss`` is the localisation term (:760-764) when
+    ``localisations`` / ``glocalisations`` [n,4] are given, else None."""
     g = as_cuda(gclasses, torch.int64)
     dev, shape = g.device, tuple(g.shape)
     o = as_cuda(objness_pred, torch.float32, dev)
@@ -614,17 +616,27 @@ def loss_masks(gclasses, objness_pred, rand_objness, rand_cls, objness_threshold
     n = g.numel()
     if not (o.numel() == n and r1.numel() == n and r2.numel() == n):
         raise ValueError('gclasses, objness_pred and the two random draws must have the same number of elements')
+    if (localisations is None) != (glocalisations is None):
+        raise ValueError('localisations and glocalisations go together')
+    lc = gl = loss = None
+    if localisations is not None:
+        lc = as_cuda(localisations, torch.float32, dev).reshape(-1, 4)
+        gl = as_cuda(glocalisations, torch.float32, dev).reshape(-1, 4)
+        if not (lc.shape[0] == n and gl.shape[0] == n):
+            raise ValueError('localisations / glocalisations must be [n,4]')
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
     fo = torch.empty(shape, dtype=torch.uint8, device=dev)
     lab = torch.empty(shape, dtype=torch.int32, device=dev)
     cp = torch.empty(shape, dtype=torch.uint8, device=dev)
     fc = torch.empty(shape, dtype=torch.uint8, device=dev)
     cnt = torch.empty((4,), dtype=torch.float32, device=dev)
     L = _ffi.lib()
-    ws = _workspace('loss', L.ronk_loss_workspace_bytes(), False, dev)
+    ws = _workspace('loss', L.ronk_loss_workspace_bytes(), True, dev)       # zeroed once; every call restores it
     with torch.cuda.device(dev):
         _ffi.check(L.ronk_loss_masks(_ptr(g), _ptr(o), _ptr(r1), _ptr(r2), n, float(objness_threshold), float(negative_ratio),
-                                     _ptr(fo), _ptr(lab), _ptr(cp), _ptr(fc), _ptr(cnt), _ptr(ws), _stream()))
-    return fo.view(torch.bool), lab, cp.view(torch.bool), fc.view(torch.bool), cnt
+                                     _ptr(fo), _ptr(lab), _ptr(cp), _ptr(fc), _ptr(cnt), _ptr(lc), _ptr(gl), float(sigma),
+                                     float(beta), _ptr(loss), _ptr(ws), _stream()))
+    return fo.view(torch.bool), lab, cp.view(torch.bool), fc.view(torch.bool), cnt, (loss[0] if loss is not None else None)
 
 
 def smooth_l1(bbox_pred, bbox_targets, inside_weight=1., outside_weight=1., sigma=1.):
@@ -651,7 +663,7 @@ def localization_loss(localisations, glocalisations, cls_positive_mask, sigma=3.
         raise ValueError('localisations / glocalisations [n,4] and cls_positive_mask [n] expected')
     out = torch.empty((1,), dtype=torch.float32, device=a.device)
     L = _ffi.lib()
-    ws = _workspace('loss', L.ronk_loss_workspace_bytes(), False, a.device)
+    ws = _workspace('loss', L.ronk_loss_workspace_bytes(), True, a.device)
     with torch.cuda.device(a.device):
         _ffi.check(L.ronk_localization_loss(_ptr(a), _ptr(b), _ptr(m), int(a.shape[0]), float(sigma), float(beta), _ptr(out),
                                             _ptr(ws), _stream()))

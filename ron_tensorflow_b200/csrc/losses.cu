@@ -2,44 +2,24 @@
 // Reference: nets/ron_vgg_320.py:686-740 (positive / negative masks, random negative sampling for the
 // objectness loss and for the objectness-gated class loss), :760-764 (localisation loss) and
 // nets/custom_layers.py:31-50 (modified_smooth_l1).
-//   loss_count_kernel   the four example counts (positives, negatives, class positives, class negatives):
-//                       ballot + popc per warp, one atomic per block and counter;
-//   loss_mask_kernel    selection probabilities from the counts in the reference's float32 / int32 steps,
-//                       then the four masks; the two tf.random_uniform draws are inputs;
+//   loss_fused_kernel   ONE cooperative launch (a grid that is co-resident, 8 CTAs per SM): pass 1 counts the
+//                       four example classes (positives, negatives, class positives, class negatives; ballot +
+//                       popc per warp, one atomic per block and counter), grid.sync(), pass 2 derives the
+//                       selection probabilities in the reference's float32 / int32 steps, writes the four masks
+//                       (the second read of the labels comes from L2) and, when the localisations are given,
+//                       accumulates the localisation term of the class positives; the CTA that finishes last
+//                       writes counts + loss and restores the workspace to zero.  The two tf.random_uniform
+//                       draws are inputs;
 //   smooth_l1_kernel    element-wise modified_smooth_l1, one rounding per op;
 //   loc_loss_kernel / loc_loss_finish_kernel   beta * mean over the class positives of the row sums,
 //                       accumulated in double (the reference's reduction order is unspecified).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
-namespace ronk {
+namespace cg = cooperative_groups;
 
-__global__ void __launch_bounds__(256)
-loss_count_kernel(const long long* __restrict__ gclasses, const float* __restrict__ objness, long long n, float obj_thr,
-                  unsigned* __restrict__ counts) {
-    __shared__ unsigned s_c[4];
-    if (threadIdx.x < 4) s_c[threadIdx.x] = 0u;
-    __syncthreads();
-    const unsigned full = 0xffffffffu;
-    unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    // whole warps iterate together (the ballots need every lane): round the bound up to a warp
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
-        const long long i = i0 + (threadIdx.x & 31);
-        const bool in = i < n;
-        const long long g = in ? gclasses[i] : -1;
-        const bool om = in && objness[i] > obj_thr;
-        const bool pos = g > 0, neg = g == 0;
-        c0 += __popc(__ballot_sync(full, pos));
-        c1 += __popc(__ballot_sync(full, neg));
-        c2 += __popc(__ballot_sync(full, pos && om));
-        c3 += __popc(__ballot_sync(full, neg && om));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_c[0], c0); atomicAdd(&s_c[1], c1); atomicAdd(&s_c[2], c2); atomicAdd(&s_c[3], c3);
-    }
-    __syncthreads();
-    if (threadIdx.x < 4 && s_c[threadIdx.x]) atomicAdd(counts + threadIdx.x, s_c[threadIdx.x]);
-}
+namespace ronk {
 
 // tfe.safe_divide(cast(min(int32(ratio * n_pos), int32(n_neg)), f32), n_neg)   (ron_vgg_320.py:700-705)
 __device__ __forceinline__ float select_prob(float ratio, unsigned n_pos, unsigned n_neg) {
@@ -47,29 +27,6 @@ __device__ __forceinline__ float select_prob(float ratio, unsigned n_pos, unsign
     const int want = (int)(ratio * fp);
     const int sel = min(want, (int)fn);
     return fn > 0.f ? (float)sel / fn : 0.f;
-}
-
-__global__ void __launch_bounds__(256)
-loss_mask_kernel(const long long* __restrict__ gclasses, const float* __restrict__ objness,
-                 const float* __restrict__ rand_obj, const float* __restrict__ rand_cls, long long n, float obj_thr,
-                 float ratio, const unsigned* __restrict__ counts, uint8_t* __restrict__ final_obj,
-                 int* __restrict__ obj_label, uint8_t* __restrict__ cls_pos, uint8_t* __restrict__ final_cls,
-                 float* __restrict__ out_counts) {
-    const float p_obj = select_prob(ratio, counts[0], counts[1]);
-    const float p_cls = select_prob(ratio, counts[2], counts[3]);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && out_counts) {
-        for (int k = 0; k < 4; ++k) out_counts[k] = (float)counts[k];
-    }
-    if (i >= n) return;
-    const long long g = gclasses[i];
-    const bool pos = g > 0, neg = g == 0;
-    const bool om = objness[i] > obj_thr;
-    const bool cp = pos && om, cn = om && neg;
-    final_obj[i] = ((neg && rand_obj[i] < p_obj) || pos) ? 1 : 0;
-    obj_label[i] = pos ? 1 : 0;
-    cls_pos[i] = cp ? 1 : 0;
-    final_cls[i] = ((cn && rand_cls[i] < p_cls) || cp) ? 1 : 0;
 }
 
 struct SmoothL1 {
@@ -82,6 +39,106 @@ struct SmoothL1 {
         return out_w * (o1 * sign + o2 * fabsf(sign - 1.f));
     }
 };
+
+struct LossParams {
+    const long long* gclasses;
+    const float* objness;
+    const float* rand_obj;
+    const float* rand_cls;
+    long long n;
+    float obj_thr, ratio;
+    uint8_t* final_obj;
+    int* obj_label;
+    uint8_t* cls_pos;
+    uint8_t* final_cls;
+    float* out_counts;          // [4] or NULL
+    const float4* loc;          // [n] or NULL: no localisation term
+    const float4* gloc;
+    SmoothL1 f;
+    float beta;
+    float* out_loss;            // [1] or NULL
+    unsigned* counts;           // ws: [4] example counts, [4] = CTAs finished      (zero between calls)
+    double* acc;                // ws: [0] sum of row losses, [1] class positives   (zero between calls)
+};
+
+__global__ void __launch_bounds__(256, 8)
+loss_fused_kernel(const __grid_constant__ LossParams p) {
+    __shared__ unsigned s_c[4];
+    __shared__ double s_sum[8];
+    __shared__ int s_last;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (threadIdx.x < 4) s_c[threadIdx.x] = 0u;
+    __syncthreads();
+    // ---- pass 1: counts.  Whole warps iterate together (the ballots need every lane).
+    {
+        unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        for (long long i0 = (long long)blockIdx.x * blockDim.x + warp * 32; i0 < p.n; i0 += stride) {
+            const long long i = i0 + lane;
+            const bool in = i < p.n;
+            const long long g = in ? p.gclasses[i] : -1;
+            const bool om = in && p.objness[i] > p.obj_thr;
+            const bool pos = g > 0, neg = g == 0;
+            c0 += __popc(__ballot_sync(full, pos));
+            c1 += __popc(__ballot_sync(full, neg));
+            c2 += __popc(__ballot_sync(full, pos && om));
+            c3 += __popc(__ballot_sync(full, neg && om));
+        }
+        if (lane == 0) { atomicAdd(&s_c[0], c0); atomicAdd(&s_c[1], c1); atomicAdd(&s_c[2], c2); atomicAdd(&s_c[3], c3); }
+        __syncthreads();
+        if (threadIdx.x < 4 && s_c[threadIdx.x]) atomicAdd(p.counts + threadIdx.x, s_c[threadIdx.x]);
+    }
+    cg::this_grid().sync();
+    // ---- pass 2: masks (+ localisation term of the class positives)
+    unsigned cnt[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt[k] = __ldcg(p.counts + k);
+    const float p_obj = select_prob(p.ratio, cnt[0], cnt[1]);
+    const float p_cls = select_prob(p.ratio, cnt[2], cnt[3]);
+    double sum = 0.;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const long long g = p.gclasses[i];
+        const bool pos = g > 0, neg = g == 0;
+        const bool om = p.objness[i] > p.obj_thr;
+        const bool cp = pos && om, cn = om && neg;
+        p.final_obj[i] = ((neg && p.rand_obj[i] < p_obj) || pos) ? 1 : 0;
+        p.obj_label[i] = pos ? 1 : 0;
+        p.cls_pos[i] = cp ? 1 : 0;
+        p.final_cls[i] = ((cn && p.rand_cls[i] < p_cls) || cp) ? 1 : 0;
+        if (p.loc && cp) {
+            const float4 a = p.loc[i], b = p.gloc[i];
+            sum += (double)p.f(a.x, b.x) + (double)p.f(a.y, b.y) + (double)p.f(a.z, b.z) + (double)p.f(a.w, b.w);
+        }
+    }
+    if (p.loc) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
+        if (lane == 0) s_sum[warp] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (p.loc) {
+            for (int w = 1; w < 8; ++w) sum += s_sum[w];
+            if (sum != 0.) atomicAdd(p.acc, sum);
+        }
+        __threadfence();
+        s_last = atomicAdd(p.counts + 4, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        if (p.out_counts)
+            for (int k = 0; k < 4; ++k) p.out_counts[k] = (float)cnt[k];
+        if (p.out_loss) {
+            // tf.cond(n_cls_positives > 0, beta * reduce_mean(...), 0)   (ron_vgg_320.py:764)
+            const double tot = __ldcg(p.acc);
+            p.out_loss[0] = (p.loc && cnt[2] > 0u) ? (float)((double)p.beta * (tot / (double)cnt[2])) : 0.f;
+        }
+        for (int k = 0; k < 5; ++k) p.counts[k] = 0u;
+        p.acc[0] = 0.;
+    }
+}
 
 __global__ void __launch_bounds__(256)
 smooth_l1_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long count, SmoothL1 f,
@@ -137,29 +194,62 @@ static SmoothL1 make_smooth_l1(float inside_w, float outside_w, double sigma) {
 
 using namespace ronk;
 
-extern "C" size_t ronk_loss_workspace_bytes(void) { return 32; }
+extern "C" size_t ronk_loss_workspace_bytes(void) { return 64; }
+
+extern "C" int ronk_loss_workspace_init(void* ws, void* stream) {
+    RONK_REQUIRE(ws != nullptr, RONK_EINVAL, "ronk_loss_workspace_init: NULL workspace");
+    RONK_CUDA(cudaMemsetAsync(ws, 0, 64, (cudaStream_t)stream));
+    return RONK_OK;
+}
 
 extern "C" int ronk_loss_masks(const int64_t* gclasses, const float* objness_pred, const float* rand_objness,
                                const float* rand_cls, long long n, float objness_threshold, float negative_ratio,
                                uint8_t* out_final_objness, int32_t* out_objness_label, uint8_t* out_cls_positive,
-                               uint8_t* out_final_cls, float* out_counts, void* ws, void* stream) {
+                               uint8_t* out_final_cls, float* out_counts, const float* localisations,
+                               const float* glocalisations, double sigma, float beta, float* out_loss, void* ws,
+                               void* stream) {
     RONK_REQUIRE(n >= 0 && ws, RONK_EINVAL, "ronk_loss_masks: bad argument");
     RONK_REQUIRE(n < (1ll << 24), RONK_ELIMIT, "ronk_loss_masks: the reference counts in float32: n must stay below 2^24");
     RONK_REQUIRE(n == 0 || (gclasses && objness_pred && rand_objness && rand_cls && out_final_objness && out_objness_label &&
                             out_cls_positive && out_final_cls),
                  RONK_EINVAL, "ronk_loss_masks: NULL pointer argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    unsigned* counts = (unsigned*)ws;
-    RONK_CUDA(cudaMemsetAsync(counts, 0, 16, st));
-    if (n > 0) {
-        const unsigned blocks = (unsigned)((n + 255) / 256);
-        loss_count_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>((const long long*)gclasses, objness_pred, n,
-                                                                           objness_threshold, counts);
-        RONK_LAUNCHED();
-    }
-    loss_mask_kernel<<<n > 0 ? (unsigned)((n + 255) / 256) : 1u, 256, 0, st>>>(
-        (const long long*)gclasses, objness_pred, rand_objness, rand_cls, n, objness_threshold, negative_ratio, counts,
-        out_final_objness, out_objness_label, out_cls_positive, out_final_cls, out_counts);
+    RONK_REQUIRE((localisations == nullptr) == (glocalisations == nullptr), RONK_EINVAL,
+                 "ronk_loss_masks: localisations and glocalisations go together");
+    RONK_REQUIRE(!localisations || (sigma > 0. && ((uintptr_t)localisations % 16) == 0 && ((uintptr_t)glocalisations % 16) == 0),
+                 RONK_EINVAL, "ronk_loss_masks: sigma must be positive and the box pointers 16-byte aligned");
+    RONK_REQUIRE(((uintptr_t)ws % 8) == 0, RONK_EINVAL, "ronk_loss_masks: ws must be 8-byte aligned");
+    LossParams p;
+    p.gclasses = (const long long*)gclasses;
+    p.objness = objness_pred;
+    p.rand_obj = rand_objness;
+    p.rand_cls = rand_cls;
+    p.n = n;
+    p.obj_thr = objness_threshold;
+    p.ratio = negative_ratio;
+    p.final_obj = out_final_objness;
+    p.obj_label = out_objness_label;
+    p.cls_pos = out_cls_positive;
+    p.final_cls = out_final_cls;
+    p.out_counts = out_counts;
+    p.loc = (const float4*)localisations;
+    p.gloc = (const float4*)glocalisations;
+    p.f = make_smooth_l1(1.f, 1.f, localisations ? sigma : 1.);
+    p.beta = beta;
+    p.out_loss = out_loss;
+    p.counts = (unsigned*)ws;
+    p.acc = (double*)((char*)ws + 32);
+    int dev = 0, sms = 0, per_sm = 0;
+    RONK_CUDA(cudaGetDevice(&dev));
+    RONK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RONK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_fused_kernel, 256, 0));
+    RONK_REQUIRE(per_sm >= 1, RONK_ECUDA, "ronk_loss_masks: the kernel does not fit on an SM");
+    long long blocks = (n + 255) / 256;
+    const long long resident = (long long)sms * per_sm;        // grid.sync() needs every CTA resident
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
+    void* args[] = {(void*)&p};
+    RONK_CUDA(cudaLaunchCooperativeKernel((const void*)loss_fused_kernel, dim3((unsigned)blocks), dim3(256), args, 0,
+                                          (cudaStream_t)stream));
     RONK_LAUNCHED();
     return RONK_OK;
 }
@@ -182,7 +272,7 @@ extern "C" int ronk_localization_loss(const float* localisations, const float* g
     RONK_REQUIRE(((uintptr_t)localisations % 16) == 0 && ((uintptr_t)glocalisations % 16) == 0 && ((uintptr_t)ws % 8) == 0,
                  RONK_EINVAL, "ronk_localization_loss: box pointers must be 16-byte aligned, ws 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    double* acc = (double*)ws + 2;                      // bytes 16..31 of the workspace
+    double* acc = (double*)((char*)ws + 48);             // bytes 48..63: not shared with ronk_loss_masks
     RONK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
     if (n > 0) {
         const unsigned blocks = (unsigned)((n + 255) / 256);

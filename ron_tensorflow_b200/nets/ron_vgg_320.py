@@ -198,14 +198,15 @@ def _nms_to_dicts(s, b, nms_threshold, keep_top_k, mode='min'):
 # RON loss: example masks + localisation term (reference :635-771)
 # =========================================================================== #
 def ron_loss_masks(gclasses, objness_pred, rand_objness=None, rand_cls=None, objness_threshold=0.03,
-                   negative_ratio=3., generator=None):
+                   negative_ratio=3., generator=None, localisations=None, glocalisations=None, beta=1. / 3):
     """reference nets/ron_vgg_320.py:686-740.  ``gclasses`` / ``objness_pred``: the encode labels and the
     objectness scores, flat or lists over layers (flattened and concatenated like :660-675).  The two
     ``tf.random_uniform`` draws of the reference (:705, :738) are ``rand_objness`` / ``rand_cls``; when
     omitted they are drawn on the device (``generator``: optional torch.Generator).
     Returns a dict: ``final_neg_mask_objness``, ``objness_pred_label`` (int32), ``cls_positive_mask``,
     ``final_cls_neg_mask_objness`` (bool tensors) and ``counts`` = float32 [n_positives, n_negtives,
-    n_cls_positives, n_cls_negtives]."""
+    n_cls_positives, n_cls_negtives].  With ``localisations`` / ``glocalisations`` (flat [n,4] or lists over
+    layers) the same launch also yields ``localization_loss`` (:760-764, see ron_localization_loss)."""
     def flat(x, dtype):
         if isinstance(x, (list, tuple)):
             return torch.cat([core.as_cuda(t, dtype).reshape(-1) for t in x], 0)
@@ -216,10 +217,20 @@ def ron_loss_masks(gclasses, objness_pred, rand_objness=None, rand_cls=None, obj
         rand_objness = torch.rand(g.shape, device=g.device, dtype=torch.float32, generator=generator)
     if rand_cls is None:
         rand_cls = torch.rand(g.shape, device=g.device, dtype=torch.float32, generator=generator)
-    fo, lab, cp, fc, cnt = core.loss_masks(g, o, flat(rand_objness, torch.float32), flat(rand_cls, torch.float32),
-                                           objness_threshold, negative_ratio)
-    return dict(final_neg_mask_objness=fo, objness_pred_label=lab, cls_positive_mask=cp,
-                final_cls_neg_mask_objness=fc, counts=cnt)
+    def flat4(x):
+        if x is None:
+            return None
+        if isinstance(x, (list, tuple)):
+            return torch.cat([core.as_cuda(t, torch.float32).reshape(-1, 4) for t in x], 0)
+        return core.as_cuda(x, torch.float32).reshape(-1, 4)
+    fo, lab, cp, fc, cnt, loss = core.loss_masks(g, o, flat(rand_objness, torch.float32), flat(rand_cls, torch.float32),
+                                                 objness_threshold, negative_ratio, flat4(localisations),
+                                                 flat4(glocalisations), 3., beta)
+    out = dict(final_neg_mask_objness=fo, objness_pred_label=lab, cls_positive_mask=cp,
+               final_cls_neg_mask_objness=fc, counts=cnt)
+    if loss is not None:
+        out['localization_loss'] = loss
+    return out
 
 
 def ron_localization_loss(localisations, glocalisations, cls_positive_mask, beta=1. / 3, sigma=3.):

@@ -88,6 +88,12 @@ def test_cuda_matches_reference_ron_losses(golden, tag):
     got = float(ron_vgg_320.ron_localization_loss(loc, gl, m['cls_positive_mask']))
     want = float(O.ron_localization_loss(loc, gl, ref['cls_positive_mask']))
     assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+    # the fused form (masks + localisation term in one launch), twice: the workspace must come back zeroed
+    for _ in range(2):
+        f = ron_vgg_320.ron_loss_masks(gcls, obj, r1, r2, objness_threshold=0.03, localisations=loc, glocalisations=gl)
+        assert abs(float(f['localization_loss']) - want) <= 1e-5 * abs(want)
+        for k in MASKS:
+            eq(f[k].to('cpu').numpy().astype(bool), _unpack(g, tag, k, n), k + ' (fused)')
 
 
 @pytest.mark.gpu
