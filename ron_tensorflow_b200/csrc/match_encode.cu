@@ -218,6 +218,24 @@ __device__ __forceinline__ void sweep(const float4* s_box, const float* s_area, 
     }
 }
 
+#ifdef RONK_ENC_TRACE
+// profiling build only (tools/enc_trace.py): per CTA 8 words {start ns, SM id, end ns, after staging, after the
+// sweep, after the output stores, after the tile counter, unused}
+__device__ unsigned long long* g_enc_trace;
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RONK_TRACE_MARK(k)                                                                          \
+    do {                                                                                            \
+        if (g_enc_trace && threadIdx.x == 0)                                                        \
+            g_enc_trace[8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + (k)] = trace_now();     \
+    } while (0)
+#else
+#define RONK_TRACE_MARK(k) do { } while (0)
+#endif
+
 constexpr int kEncThreads = 128;
 constexpr int kEncPrefetch = 4;     // flat anchors per thread whose compact index is fetched before the sweep
 
@@ -302,6 +320,7 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
         wx1 = fmaxf(wx1, __shfl_xor_sync(full, wx1, o));
     }
     nice = __syncthreads_and(nice && p.anchors_nice) != 0;
+    RONK_TRACE_MARK(3);
 
     float best[kEncApt];
     int bestg[kEncApt];
@@ -319,6 +338,7 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
         s_mg[part][set * kEncSet + j * 32 + lane] = bestg[j];
     }
     __syncthreads();
+    RONK_TRACE_MARK(4);
 
     for (int g = tid; g < G; g += kEncThreads) {
         u64 v = s_best[g];
@@ -378,12 +398,14 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
     // ---- publish; the last item of the image applies the per-GT forcing.  Barrier first, then
     // one thread fences and bumps the counter (release pattern of a grid-wide barrier).
     __syncthreads();
+    RONK_TRACE_MARK(5);
     if (tid == 0) {
         __threadfence();
         unsigned prev = atomicAdd(p.ws_count + b, 1u);
         s_last = (prev == (unsigned)p.tiles - 1u) ? 1 : 0;
     }
     __syncthreads();
+    RONK_TRACE_MARK(6);
     if (s_last) {
         __threadfence();
         // s_best (8 B per GT slot) is free now: reuse it as two int arrays
@@ -395,11 +417,24 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
 __global__ void __launch_bounds__(kEncThreads, 8)
 match_encode_kernel(const __grid_constant__ EncodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+#ifdef RONK_ENC_TRACE
+    unsigned long long* tr = g_enc_trace ? g_enc_trace + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    if (tr && threadIdx.x == 0) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        tr[0] = trace_now();
+        tr[1] = sm;
+    }
+#endif
     const int4 item = __ldg(p.items + blockIdx.y);
     if (item.w == 4)
         encode_item<1, 4>(p, smem, blockIdx.x, item.x, item.y, item.z);
     else
         encode_item<4, 1>(p, smem, blockIdx.x, item.x, item.y, item.z);
+#ifdef RONK_ENC_TRACE
+    __syncthreads();
+    if (tr && threadIdx.x == 0) tr[2] = trace_now();
+#endif
 }
 
 __global__ void zero_u32_kernel(unsigned* p, size_t n) {
@@ -410,6 +445,13 @@ __global__ void zero_u32_kernel(unsigned* p, size_t n) {
 }  // namespace ronk
 
 using namespace ronk;
+
+#ifdef RONK_ENC_TRACE
+extern "C" int ronk_debug_set_enc_trace(void* buf) {
+    RONK_CUDA(cudaMemcpyToSymbol(g_enc_trace, &buf, sizeof(buf)));
+    return RONK_OK;
+}
+#endif
 
 extern "C" size_t ronk_encode_workspace_bytes(int B, int Gmax) {
     if (B < 1 || Gmax < 1) return 0;
