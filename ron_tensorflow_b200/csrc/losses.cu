@@ -2,9 +2,10 @@
 // Reference: nets/ron_vgg_320.py:686-740 (positive / negative masks, random negative sampling for the
 // objectness loss and for the objectness-gated class loss), :760-764 (localisation loss) and
 // nets/custom_layers.py:31-50 (modified_smooth_l1).
-//   loss_fused_kernel   ONE cooperative launch (a grid that is co-resident, 8 CTAs per SM): pass 1 counts the
-//                       four example classes (positives, negatives, class positives, class negatives; ballot +
-//                       popc per warp, one atomic per block and counter), grid.sync(), pass 2 derives the
+//   loss_fused_kernel   ONE cooperative launch (a co-resident grid), 4 elements per thread
+//                       and step with 16-byte accesses: pass 1 counts the four example classes (positives,
+//                       negatives, class positives, class negatives; warp reduction, one atomic per block and
+//                       counter), grid.sync(), pass 2 derives the
 //                       selection probabilities in the reference's float32 / int32 steps, writes the four masks
 //                       (the second read of the labels comes from L2) and, when the localisations are given,
 //                       accumulates the localisation term of the class positives; the CTA that finishes last
@@ -61,7 +62,11 @@ struct LossParams {
     double* acc;                // ws: [0] sum of row losses, [1] class positives   (zero between calls)
 };
 
-__global__ void __launch_bounds__(256, 8)
+// VEC: every array is 16-byte aligned (4-byte for the uint8 masks): a thread handles 4 consecutive elements
+// per step with 16-byte loads / stores, so that all of a thread's loads of a pass are in flight together; the
+// (n % 4) tail and the unaligned case go through the scalar path.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 4)
 loss_fused_kernel(const __grid_constant__ LossParams p) {
     __shared__ unsigned s_c[4];
     __shared__ double s_sum[8];
@@ -69,22 +74,26 @@ loss_fused_kernel(const __grid_constant__ LossParams p) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long quads = VEC ? (p.n >> 2) : 0;
     if (threadIdx.x < 4) s_c[threadIdx.x] = 0u;
     __syncthreads();
-    // ---- pass 1: counts.  Whole warps iterate together (the ballots need every lane).
+    // ---- pass 1: counts
     {
         unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        for (long long i0 = (long long)blockIdx.x * blockDim.x + warp * 32; i0 < p.n; i0 += stride) {
-            const long long i = i0 + lane;
-            const bool in = i < p.n;
-            const long long g = in ? p.gclasses[i] : -1;
-            const bool om = in && p.objness[i] > p.obj_thr;
-            const bool pos = g > 0, neg = g == 0;
-            c0 += __popc(__ballot_sync(full, pos));
-            c1 += __popc(__ballot_sync(full, neg));
-            c2 += __popc(__ballot_sync(full, pos && om));
-            c3 += __popc(__ballot_sync(full, neg && om));
+        auto count = [&](long long g, float o) {
+            const bool om = o > p.obj_thr, pos = g > 0, neg = g == 0;
+            c0 += pos; c1 += neg; c2 += pos && om; c3 += neg && om;
+        };
+        for (long long q = gtid; q < quads; q += stride) {
+            const longlong2 ga = reinterpret_cast<const longlong2*>(p.gclasses)[2 * q];
+            const longlong2 gb = reinterpret_cast<const longlong2*>(p.gclasses)[2 * q + 1];
+            const float4 o = reinterpret_cast<const float4*>(p.objness)[q];
+            count(ga.x, o.x); count(ga.y, o.y); count(gb.x, o.z); count(gb.y, o.w);
         }
+        for (long long i = 4 * quads + gtid; i < p.n; i += stride) count(p.gclasses[i], p.objness[i]);
+        c0 = __reduce_add_sync(full, c0); c1 = __reduce_add_sync(full, c1);
+        c2 = __reduce_add_sync(full, c2); c3 = __reduce_add_sync(full, c3);
         if (lane == 0) { atomicAdd(&s_c[0], c0); atomicAdd(&s_c[1], c1); atomicAdd(&s_c[2], c2); atomicAdd(&s_c[3], c3); }
         __syncthreads();
         if (threadIdx.x < 4 && s_c[threadIdx.x]) atomicAdd(p.counts + threadIdx.x, s_c[threadIdx.x]);
@@ -97,19 +106,39 @@ loss_fused_kernel(const __grid_constant__ LossParams p) {
     const float p_obj = select_prob(p.ratio, cnt[0], cnt[1]);
     const float p_cls = select_prob(p.ratio, cnt[2], cnt[3]);
     double sum = 0.;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-        const long long g = p.gclasses[i];
-        const bool pos = g > 0, neg = g == 0;
-        const bool om = p.objness[i] > p.obj_thr;
+    // returns {final_obj, obj_label, cls_pos, final_cls} bits 0..3
+    auto masks = [&](long long i, long long g, float o, float r1, float r2) -> unsigned {
+        const bool pos = g > 0, neg = g == 0, om = o > p.obj_thr;
         const bool cp = pos && om, cn = om && neg;
-        p.final_obj[i] = ((neg && p.rand_obj[i] < p_obj) || pos) ? 1 : 0;
-        p.obj_label[i] = pos ? 1 : 0;
-        p.cls_pos[i] = cp ? 1 : 0;
-        p.final_cls[i] = ((cn && p.rand_cls[i] < p_cls) || cp) ? 1 : 0;
         if (p.loc && cp) {
             const float4 a = p.loc[i], b = p.gloc[i];
             sum += (double)p.f(a.x, b.x) + (double)p.f(a.y, b.y) + (double)p.f(a.z, b.z) + (double)p.f(a.w, b.w);
         }
+        return (((neg && r1 < p_obj) || pos) ? 1u : 0u) | (pos ? 2u : 0u) | (cp ? 4u : 0u) |
+               (((cn && r2 < p_cls) || cp) ? 8u : 0u);
+    };
+    for (long long q = gtid; q < quads; q += stride) {
+        const longlong2 ga = reinterpret_cast<const longlong2*>(p.gclasses)[2 * q];
+        const longlong2 gb = reinterpret_cast<const longlong2*>(p.gclasses)[2 * q + 1];
+        const float4 o = reinterpret_cast<const float4*>(p.objness)[q];
+        const float4 r1 = reinterpret_cast<const float4*>(p.rand_obj)[q];
+        const float4 r2 = reinterpret_cast<const float4*>(p.rand_cls)[q];
+        const unsigned m0 = masks(4 * q, ga.x, o.x, r1.x, r2.x), m1 = masks(4 * q + 1, ga.y, o.y, r1.y, r2.y);
+        const unsigned m2 = masks(4 * q + 2, gb.x, o.z, r1.z, r2.z), m3 = masks(4 * q + 3, gb.y, o.w, r1.w, r2.w);
+        auto pack = [&](int bit) {
+            return make_uchar4((m0 >> bit) & 1u, (m1 >> bit) & 1u, (m2 >> bit) & 1u, (m3 >> bit) & 1u);
+        };
+        reinterpret_cast<uchar4*>(p.final_obj)[q] = pack(0);
+        reinterpret_cast<int4*>(p.obj_label)[q] = make_int4((m0 >> 1) & 1, (m1 >> 1) & 1, (m2 >> 1) & 1, (m3 >> 1) & 1);
+        reinterpret_cast<uchar4*>(p.cls_pos)[q] = pack(2);
+        reinterpret_cast<uchar4*>(p.final_cls)[q] = pack(3);
+    }
+    for (long long i = 4 * quads + gtid; i < p.n; i += stride) {
+        const unsigned m = masks(i, p.gclasses[i], p.objness[i], p.rand_obj[i], p.rand_cls[i]);
+        p.final_obj[i] = m & 1u;
+        p.obj_label[i] = (m >> 1) & 1u;
+        p.cls_pos[i] = (m >> 2) & 1u;
+        p.final_cls[i] = (m >> 3) & 1u;
     }
     if (p.loc) {
 #pragma unroll
@@ -238,18 +267,23 @@ extern "C" int ronk_loss_masks(const int64_t* gclasses, const float* objness_pre
     p.out_loss = out_loss;
     p.counts = (unsigned*)ws;
     p.acc = (double*)((char*)ws + 32);
+    const uintptr_t all16 = (uintptr_t)gclasses | (uintptr_t)objness_pred | (uintptr_t)rand_objness | (uintptr_t)rand_cls |
+                            (uintptr_t)out_objness_label;
+    const uintptr_t all4 = (uintptr_t)out_final_objness | (uintptr_t)out_cls_positive | (uintptr_t)out_final_cls;
+    const bool vec = (all16 % 16) == 0 && (all4 % 4) == 0;
+    const void* kern = vec ? (const void*)loss_fused_kernel<true> : (const void*)loss_fused_kernel<false>;
     int dev = 0, sms = 0, per_sm = 0;
     RONK_CUDA(cudaGetDevice(&dev));
     RONK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    RONK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_fused_kernel, 256, 0));
+    if (vec) RONK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_fused_kernel<true>, 256, 0));
+    else RONK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_fused_kernel<false>, 256, 0));
     RONK_REQUIRE(per_sm >= 1, RONK_ECUDA, "ronk_loss_masks: the kernel does not fit on an SM");
-    long long blocks = (n + 255) / 256;
+    long long blocks = ((vec ? (n + 3) / 4 : n) + 255) / 256;
     const long long resident = (long long)sms * per_sm;        // grid.sync() needs every CTA resident
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
     void* args[] = {(void*)&p};
-    RONK_CUDA(cudaLaunchCooperativeKernel((const void*)loss_fused_kernel, dim3((unsigned)blocks), dim3(256), args, 0,
-                                          (cudaStream_t)stream));
+    RONK_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(256), args, 0, (cudaStream_t)stream));
     RONK_LAUNCHED();
     return RONK_OK;
 }

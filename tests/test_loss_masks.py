@@ -113,6 +113,17 @@ def test_cuda_loss_masks_batch64_and_edge_cases():
     for k in MASKS:
         eq(m[k].to('cpu').numpy().astype(bool), ref[k].astype(bool), k)
     eq(m['counts'], ref['counts'], 'counts')
+    # views that are not 16-byte aligned take the scalar path; an odd length exercises the (n % 4) tail
+    def off1(x):
+        t = torch.from_numpy(np.concatenate([x[:1], x])).cuda()
+        return t[1:]
+    for m_ in (n - 1, 4099):
+        mu = ron_vgg_320.ron_loss_masks(off1(gcls[:m_]), off1(obj[:m_]), off1(r1[:m_]), off1(r2[:m_]), objness_threshold=0.1)
+        ma = ron_vgg_320.ron_loss_masks(gcls[:m_], obj[:m_], r1[:m_], r2[:m_], objness_threshold=0.1)
+        ru = O.ron_loss_masks(gcls[:m_], obj[:m_], r1[:m_], r2[:m_], 0.1, 3.)
+        for k in MASKS:
+            eq(mu[k].to('cpu').numpy().astype(bool), ru[k].astype(bool), k + ' (unaligned)')
+            eq(ma[k].to('cpu').numpy().astype(bool), ru[k].astype(bool), k + ' (odd length)')
     # lists over layers are flattened and concatenated
     cut = [1000, 50000, n - 51000]
     parts = lambda x: [torch.from_numpy(p) for p in np.split(x, np.cumsum(cut)[:-1])]

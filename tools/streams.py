@@ -34,7 +34,7 @@ d = [torch.from_numpy(x).cuda() for x in (boxes, labels, counts)]
 outs = [dict(labels=torch.empty((B, N), dtype=torch.int64, device='cuda'), loc=torch.empty((B, N, 4), device='cuda'),
              scores=torch.empty((B, N), device='cuda')) for _ in range(8)]          # 8 x 38 MB > L2
 def enc(k): core.match_encode(aset, d[0], d[1], d[2], 0.56, 0.3, out=outs[k % 8])
-for ns in (1, 2, 3, 4):
+for ns in ((1, 2, 3, 4) if 'post-only' not in sys.argv else ()):
     print('encode B=64  streams=%d  %.1f us/step' % (ns, run(enc, ns)))
 
 PB = 256
@@ -48,5 +48,5 @@ dg = [torch.from_numpy(x).cuda() for x in (gl, gb, gl * 0)]
 def post(k):
     ns, nb = net.detect(dp, dl, do, 0.03, 0.01, 0.45, [0., 0., 1., 1.], 400, 200)
     core.tpfp_match(ns, nb, dg[0], dg[1], dg[2], 0.5)
-for ns in (1, 2, 3, 4, 6):
+for ns in ((1, 2, 3, 4, 6) if 'post-only' not in sys.argv else (1, 3)):
     print('post B=256   streams=%d  %.1f us/step' % (ns, run(post, ns, steps=24, warm=4)))
