@@ -188,7 +188,9 @@ int ronk_tpfp_match(const float* det_scores, const float* det_boxes, int B, int 
  * ronk_pairwise         intersection / iou_matrix  nets/ssd_common.py:30-47     a [G,4], b [N,4] -> [G,N]
  *                       (mode 0 = intersection, 1 = IoU with 0 where the union is 0)
  * ronk_overlap_ref      bboxes_jaccard / bboxes_intersection  tf_extended/bboxes.py:527-583
- *                       ref [1 or N,4] (device) vs boxes [N,4] -> [N] (mode 0 = jaccard, 1 = intersection)
+ *                       ref [1 or N,4] (device) vs boxes [N,4] -> [N] (mode 0 = jaccard, 1 = intersection;
+ *                       2 / 3 = the NumPy flavours of nets/np_methods.py:187-227: plain IEEE quotients, union =
+ *                       (vol_ref + vol_box) - inter, intersection relative to the reference box)
  * ronk_select_mask      tf_ssd_bboxes_select_layer nets/ssd_common.py:504-549   pred [B,n,C], boxes [B,n,4]
  *                       -> scores [B,C',n], boxes [B,C',n,4] zeroed where score <= thr (C' skips ignore_class)
  * ronk_dual_max_match   do_dual_max_match          nets/ssd_common.py:49-75     overlap [G,N] -> matched int64 [N], scores [N]
@@ -282,6 +284,23 @@ int ronk_smooth_l1(const float* pred, const float* target, long long count, floa
                    float outside_weight, double sigma, float* out, void* stream);
 int ronk_localization_loss(const float* localisations, const float* glocalisations, const uint8_t* cls_positive,
                            long long n, double sigma, float beta, float* out_loss, void* ws, void* stream);
+
+/* ------------------------------------------- nets/np_methods.py (the notebooks' NumPy post-process)
+ * (decode / sort / resize reuse ronk_decode, ronk_sort_topk, ronk_bboxes_resize)
+ * ronk_np_select_mask    ssd_bboxes_select_layer  nets/np_methods.py:86-97   pred [n,C] -> keep mask over the
+ *                        n*(C-1) (anchor, class >= 1) pairs in row-major order (pred > threshold), or over the n
+ *                        anchors (argmax > 0) when use_threshold == 0 (select_threshold None / 0)
+ * ronk_np_select_gather  same lines: classes int64 [m], scores [m], boxes [m,4] of the kept pairs idx[m]
+ * ronk_np_clip           bboxes_clip  nets/np_methods.py:147-158   four max / min, bbox_ref on the host
+ * ronk_np_nms            bboxes_nms   nets/np_methods.py:229-242 (bboxes_jaccard :181-201)   class-aware greedy
+ *                        NMS on score-sorted boxes -> keep flags uint8 [n]; one launch, one CTA */
+int ronk_np_select_mask(const float* pred, long long n, int C, int use_threshold, float threshold,
+                        uint8_t* out_mask, void* stream);
+int ronk_np_select_gather(const float* pred, const float* boxes, int C, int use_threshold, const int32_t* idx,
+                          int m, int64_t* out_classes, float* out_scores, float* out_boxes, void* stream);
+int ronk_np_clip(const float* bbox_ref_host /*[4]*/, const float* boxes, long long n, float* out_boxes, void* stream);
+int ronk_np_nms(const int64_t* classes, const float* boxes, int n, float nms_threshold, uint8_t* out_keep,
+                void* stream);
 
 /* number of kernel launches issued by this library in this process since load
  * (bench.py reports it as gpu_launches) */

@@ -69,6 +69,11 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     'ronk_group_by_label': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ronk_mark_positions': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ronk_np_select_mask': (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'ronk_np_select_gather': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    'ronk_np_clip': (c_int, [P(c_float), c_void_p, c_longlong, c_void_p, c_void_p]),
+    'ronk_np_nms': (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     'ronk_loss_workspace_bytes': (c_size_t, []),
     'ronk_loss_workspace_init': (c_int, [c_void_p, c_void_p]),
     'ronk_loss_masks': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_void_p, c_void_p,

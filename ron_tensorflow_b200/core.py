@@ -433,7 +433,8 @@ def overlap_ref(bbox_ref, boxes, what):
     out = torch.empty((b.shape[0],), dtype=torch.float32, device=b.device)
     with torch.cuda.device(b.device):
         _ffi.check(_ffi.lib().ronk_overlap_ref(_ptr(r), int(r.shape[0]), _ptr(b), int(b.shape[0]),
-                                               0 if what == 'jaccard' else 1, _ptr(out), _stream()))
+                                               {'jaccard': 0, 'intersection': 1, 'jaccard_np': 2,
+                                                'intersection_np': 3}[what], _ptr(out), _stream()))
     return out
 
 
@@ -599,6 +600,50 @@ def gather_i64(src, idx):
     with torch.cuda.device(src.device):
         _ffi.check(_ffi.lib().ronk_gather_i64(_ptr(src), _ptr(idx), S, N, K, _ptr(out), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- nets/np_methods.py flavour
+def np_select(pred, boxes, select_threshold):
+    """nets/np_methods.py:86-97 for one layer: pred [n,C], boxes [n,4] -> classes int64 [m], scores [m], boxes [m,4]
+    in np.where order (one entry per (anchor, class) pair above the threshold; argmax > 0 when it is None / 0)."""
+    p = as_cuda(pred, torch.float32)
+    b = as_cuda(boxes, torch.float32, p.device).reshape(-1, 4)
+    n, C = int(p.shape[0]), int(p.shape[1])
+    use = 0 if (select_threshold is None or select_threshold == 0) else 1
+    total = n * (C - 1) if use else n
+    mask = torch.empty((max(total, 1),), dtype=torch.uint8, device=p.device)
+    L = _ffi.lib()
+    with torch.cuda.device(p.device):
+        _ffi.check(L.ronk_np_select_mask(_ptr(p), n, C, use, float(select_threshold or 0.), _ptr(mask), _stream()))
+    idx = compact_indices(mask[:total])
+    m = int(idx.numel())
+    cls = torch.empty((m,), dtype=torch.int64, device=p.device)
+    sc = torch.empty((m,), dtype=torch.float32, device=p.device)
+    ob = torch.empty((m, 4), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        _ffi.check(L.ronk_np_select_gather(_ptr(p), _ptr(b), C, use, _ptr(idx), m, _ptr(cls), _ptr(sc), _ptr(ob), _stream()))
+    return cls, sc, ob
+
+
+def np_clip(bbox_ref, boxes):
+    """nets/np_methods.py:147-158."""
+    b = as_cuda(boxes, torch.float32)
+    ref = [float(v) for v in (bbox_ref.tolist() if hasattr(bbox_ref, 'tolist') else bbox_ref)]
+    out = torch.empty_like(b)
+    with torch.cuda.device(b.device):
+        _ffi.check(_ffi.lib().ronk_np_clip(_ffi.farr(ref), _ptr(b), b.numel() // 4, _ptr(out), _stream()))
+    return out
+
+
+def np_nms_keep(classes, boxes, nms_threshold):
+    """nets/np_methods.py:229-240: keep flags uint8 [n] of the class-aware greedy NMS on score-sorted boxes."""
+    c = as_cuda(classes, torch.int64)
+    b = as_cuda(boxes, torch.float32, c.device).reshape(-1, 4)
+    n = int(c.shape[0])
+    keep = torch.empty((max(n, 1),), dtype=torch.uint8, device=c.device)
+    with torch.cuda.device(c.device):
+        _ffi.check(_ffi.lib().ronk_np_nms(_ptr(c), _ptr(b), n, float(nms_threshold), _ptr(keep), _stream()))
+    return keep[:n]
 
 
 # ----------------------------------------------------------------------------- RON loss masks (SURVEY 8f rank 2)

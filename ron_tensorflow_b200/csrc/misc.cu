@@ -42,7 +42,14 @@ overlap_ref_kernel(const float4* __restrict__ ref, int ref_n, const float4* __re
     float w = fmaxf(fminf(b.w, r.w) - fmaxf(b.y, r.y), 0.f);
     float inter = h * w;
     float bvol = (b.z - b.x) * (b.w - b.y);
-    float den = (mode == 0) ? ((-inter + bvol) + (r.z - r.x) * (r.w - r.y)) : bvol;
+    float rvol = (r.z - r.x) * (r.w - r.y);
+    if (mode >= 2) {
+        // nets/np_methods.py:187-227: plain IEEE quotients, union = (vol_ref + vol_box) - inter, the
+        // intersection score is relative to the REFERENCE box
+        out[i] = __fdiv_rn(inter, mode == 2 ? ((rvol + bvol) - inter) : rvol);
+        return;
+    }
+    float den = (mode == 0) ? ((-inter + bvol) + rvol) : bvol;
     out[i] = (den > 0.f) ? inter / den : 0.f;   // tf_extended/math.py:25-38
 }
 
@@ -194,7 +201,7 @@ extern "C" int ronk_pairwise(const float* a, int G, const float* b, int N, int m
 
 extern "C" int ronk_overlap_ref(const float* ref, int ref_n, const float* boxes, int N, int mode, float* out,
                                 void* stream) {
-    RONK_REQUIRE(ref && boxes && out && N >= 1 && (ref_n == 1 || ref_n == N) && (mode == 0 || mode == 1), RONK_EINVAL,
+    RONK_REQUIRE(ref && boxes && out && N >= 1 && (ref_n == 1 || ref_n == N) && mode >= 0 && mode <= 3, RONK_EINVAL,
                  "ronk_overlap_ref: bad argument");
     RONK_REQUIRE(((uintptr_t)ref % 16) == 0 && ((uintptr_t)boxes % 16) == 0, RONK_EINVAL,
                  "ronk_overlap_ref: 16-byte alignment");

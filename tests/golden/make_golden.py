@@ -386,7 +386,59 @@ def gen_loss_masks():
     save('loss_masks', **out)
 
 
+# --------------------------------------------------------------------------- #
+# nets/np_methods.py: pure NumPy, so the UNMODIFIED reference functions run here (np.bool is restored for :232)
+# --------------------------------------------------------------------------- #
+def gen_np_methods():
+    if not hasattr(np, 'bool'):
+        np.bool = bool                      # removed in NumPy 1.24; np_methods.py:232 still spells it
+    from nets import np_methods
+    out = {}
+    net = ssd_vgg_300.SSDNet()
+    anchors = net.anchors((300, 300))
+    LS = [38 * 38 * 4, 19 * 19 * 6, 10 * 10 * 6, 5 * 5 * 6, 3 * 3 * 4, 1 * 1 * 4]
+    FS = [(38, 38), (19, 19), (10, 10), (5, 5), (3, 3), (1, 1)]
+    AP = [4, 6, 6, 6, 4, 4]
+    N = sum(LS)
+    for tag, seed, thr, nms_thr in (('a', 611, 0.5, 0.45), ('b', 612, None, 0.3), ('c', 613, 0.05, 0.45)):
+        loc, pred, _ = synth.make_predictions(seed, 1, N, 21, hot=120)
+        P = synth.split_layers(pred, LS, FS, AP)
+        Lc = synth.split_layers(loc, LS, FS, AP)
+        # The reference's decode uses np.exp in float32, whose last bit depends on the NumPy build / CPU: its boxes
+        # are kept for a tolerance check only, and the exact stages run (decode=False) on boxes from the oracle's
+        # decode (correctly rounded exp), which every platform reproduces.
+        if tag == 'a':                       # every 7th decoded row is enough for the tolerance check
+            dec_ref = [np_methods.ssd_bboxes_decode(Lc[i], anchors[i]) for i in range(len(LS))]
+            out[tag + '_decoded_7th'] = np.concatenate([d.reshape(-1, 4) for d in dec_ref]).astype(np.float32)[::7]
+        from oracle import ron_oracle as _O
+        flat = _O.decode(loc[0], _O.flat_decode_anchors(_O.anchors_all_layers(_O.SSD300)))
+        dec = synth.split_layers(flat[None], LS, FS, AP)
+        c, s_, b = np_methods.ssd_bboxes_select(P, dec, anchors, select_threshold=thr, img_shape=(300, 300), num_classes=21, decode=False)
+        sha = lambda *a: np.frombuffer(__import__('hashlib').sha256(b''.join(np.ascontiguousarray(x).tobytes() for x in a)).digest(), np.uint8)
+        # the selection can be long (15 k entries): its length and a digest of (classes int64, scores, boxes) are stored
+        out[tag + '_sel_count'] = np.array([c.shape[0]], np.int64)
+        out[tag + '_sel_sha'] = sha(c.astype(np.int64), s_.astype(np.float32), b.astype(np.float32))
+        ref = np.array([0.05, 0.1, 0.9, 0.95], np.float32)
+        b = np_methods.bboxes_clip(ref, b)
+        out[tag + '_clipped_sha'] = sha(b.astype(np.float32))
+        # np.argsort leaves the order of equal scores unspecified: the fixture must not depend on it
+        assert np.array_equal(np.argsort(-s_)[:400], np.argsort(-s_, kind='stable')[:400]), 'tied scores inside the top-k'
+        c, s_, b = np_methods.bboxes_sort(c, s_, b, top_k=400)
+        out[tag + '_sort_classes'], out[tag + '_sort_scores'], out[tag + '_sort_boxes'] = c.astype(np.int16), s_, b
+        c, s_, b = np_methods.bboxes_nms(c, s_, b, nms_threshold=nms_thr)
+        out[tag + '_nms_classes'], out[tag + '_nms_scores'], out[tag + '_nms_boxes'] = c.astype(np.int16), s_, b
+        out[tag + '_resized'] = np_methods.bboxes_resize(ref, b)
+        out[tag + '_jaccard'] = np_methods.bboxes_jaccard(b[0], b)
+        out[tag + '_intersection'] = np_methods.bboxes_intersection(b[0], b)
+        out[tag + '_cfg'] = np.array([seed, -1 if thr is None else int(round(thr * 1000)), int(round(nms_thr * 1000))], np.int64)
+        out[tag + '_in_pred_sha'] = np.frombuffer(__import__('hashlib').sha256(pred.tobytes() + loc.tobytes()).digest(), np.uint8)
+    save('np_methods', **out)
+
+
 if __name__ == '__main__':
+    if '--only-np' in sys.argv:
+        gen_np_methods()
+        sys.exit(0)
     if '--only-loss' in sys.argv:
         gen_loss_masks()
         sys.exit(0)
@@ -403,3 +455,4 @@ if __name__ == '__main__':
     gen_nms()
     gen_tpfp()
     gen_loss_masks()
+    gen_np_methods()
