@@ -302,6 +302,16 @@ int ronk_np_clip(const float* bbox_ref_host /*[4]*/, const float* boxes, long lo
 int ronk_np_nms(const int64_t* classes, const float* boxes, int n, float nms_threshold, uint8_t* out_keep,
                 void* stream);
 
+/* ------------------------------------------- datasets/voc_eval.py (offline PASCAL VOC evaluator)
+ * 
+ * ronk_voc_match   voc_eval  datasets/voc_eval.py:249-281   one class: detections float64 [nd,4] (x1,y1,x2,y2 as parsed
+ *                  from the result file) sorted by decreasing confidence and grouped by image (det_offsets int32
+ *                  [n_images+1]), ground truth float64 [ng,4] + difficult flags grouped the same way (gt_offsets),
+ *                  max_gt = the largest group -> tp / fp uint8 [nd].  All arithmetic in float64 */
+int ronk_voc_match(const double* det_boxes, const int32_t* det_offsets, const double* gt_boxes,
+                   const int32_t* gt_offsets, const uint8_t* gt_difficult, int n_images, int max_gt,
+                   double ovthresh, uint8_t* out_tp, uint8_t* out_fp, void* stream);
+
 /* number of kernel launches issued by this library in this process since load
  * (bench.py reports it as gpu_launches) */
 long long ronk_launch_count(void);

@@ -646,6 +646,29 @@ def np_nms_keep(classes, boxes, nms_threshold):
     return keep[:n]
 
 
+# ----------------------------------------------------------------------------- datasets/voc_eval.py
+def voc_match(det_boxes, det_offsets, gt_boxes, gt_offsets, gt_difficult, ovthresh=0.5):
+    """datasets/voc_eval.py:249-281 for one class (ronk_voc_match).  det_boxes float64 [nd,4] sorted by decreasing
+    confidence and grouped by image, offsets int32 [n_images+1]; returns tp, fp uint8 [nd] (CUDA)."""
+    d = as_cuda(np.ascontiguousarray(det_boxes, np.float64).reshape(-1, 4), torch.float64)
+    g = as_cuda(np.ascontiguousarray(gt_boxes, np.float64).reshape(-1, 4), torch.float64, d.device)
+    do = as_cuda(np.ascontiguousarray(det_offsets, np.int32), torch.int32, d.device)
+    go = as_cuda(np.ascontiguousarray(gt_offsets, np.int32), torch.int32, d.device)
+    gd = as_cuda(np.ascontiguousarray(gt_difficult, np.uint8), torch.uint8, d.device)
+    n_img = int(do.numel()) - 1
+    if int(go.numel()) != n_img + 1:
+        raise ValueError('det_offsets and gt_offsets must both have n_images + 1 entries')
+    sizes = np.diff(np.asarray(gt_offsets, np.int64))
+    nd = int(d.shape[0])
+    tp = torch.zeros((max(nd, 1),), dtype=torch.uint8, device=d.device)
+    fp = torch.zeros((max(nd, 1),), dtype=torch.uint8, device=d.device)
+    with torch.cuda.device(d.device):
+        _ffi.check(_ffi.lib().ronk_voc_match(_ptr(d), _ptr(do), _ptr(g), _ptr(go), _ptr(gd), n_img,
+                                             int(sizes.max()) if sizes.size else 0, float(ovthresh), _ptr(tp), _ptr(fp),
+                                             _stream()))
+    return tp[:nd], fp[:nd]
+
+
 # ----------------------------------------------------------------------------- RON loss masks (SURVEY 8f rank 2)
 def loss_masks(gclasses, objness_pred, rand_objness, rand_cls, objness_threshold=0.03, negative_ratio=3.,
                localisations=None, glocalisations=None, sigma=3., beta=1. / 3):

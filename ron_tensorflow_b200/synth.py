@@ -102,3 +102,68 @@ def make_loss_inputs(seed, batch, num_anchors=21250, num_classes=21):
     obj_logits = rng.normal(0, 1, (batch, num_anchors, 2)).astype(np.float32)
     obj_pred = (1. / (1. + np.exp(-rng.normal(-3, 2, (batch, num_anchors))))).astype(np.float32)
     return logits, loc, obj_logits, obj_pred
+
+
+VOC_CLASSES = ('aeroplane', 'bicycle', 'bird', 'boat', 'bottle', 'bus', 'car', 'cat', 'chair', 'cow', 'diningtable',
+               'dog', 'horse', 'motorbike', 'person', 'pottedplant', 'sheep', 'sofa', 'train', 'tvmonitor')
+
+
+def make_voc_eval_case(seed, n_images=40, width=500, height=375):
+    """A small synthetic PASCAL-VOC evaluation problem (reference datasets/voc_eval.py): per image a list of objects
+    {name, difficult, bbox [xmin, ymin, xmax, ymax] 1-based ints} and, per class index 1..20, per image, a float32
+    [k,5] array of detections (x1, y1, x2, y2, score) -- jittered copies of the objects plus random boxes.  The
+    scores of one class are all different to 3 decimals (the result files keep 3, and np.argsort leaves the order
+    of equal scores unspecified)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ids = ['%06d' % (i + 1) for i in range(n_images)]
+    annots = []
+    for _ in ids:
+        objs = []
+        for _ in range(int(rng.integers(1, 7))):
+            w, h = int(rng.integers(30, 250)), int(rng.integers(30, 200))
+            x0, y0 = int(rng.integers(1, width - w)), int(rng.integers(1, height - h))
+            objs.append(dict(name=VOC_CLASSES[int(rng.integers(0, 20))], difficult=int(rng.random() < 0.15),
+                             bbox=[x0, y0, x0 + w, y0 + h]))
+        annots.append(objs)
+    all_boxes = [[np.zeros((0, 5), np.float32) for _ in ids] for _ in range(21)]
+    for c in range(1, 21):
+        dets = []
+        for i, objs in enumerate(annots):
+            for o in objs:
+                if o['name'] != VOC_CLASSES[c - 1]:
+                    continue
+                for _ in range(int(rng.integers(0, 4))):                 # 0-3 detections near the object
+                    j = rng.normal(0, 12, 4)
+                    b = np.array(o['bbox'], np.float64) - 1 + j
+                    dets.append((i, b))
+            for _ in range(int(rng.integers(0, 3))):                     # and a few anywhere
+                w, h = rng.uniform(20, 300), rng.uniform(20, 250)
+                x0, y0 = rng.uniform(0, width - 20), rng.uniform(0, height - 20)
+                dets.append((i, np.array([x0, y0, x0 + w, y0 + h])))
+        scores = rng.permutation(999)[:len(dets)] + 1                    # distinct k / 1000
+        per_img = [[] for _ in ids]
+        for (i, b), sc in zip(dets, scores):
+            per_img[i].append(np.concatenate([np.round(b, 1), [sc / 1000.]]))
+        for i in range(n_images):
+            if per_img[i]:
+                all_boxes[c][i] = np.array(per_img[i], np.float32)
+    return ids, annots, all_boxes
+
+
+def write_voc_tree(voc_root, ids, annots, set_type='test'):
+    """Annotations/*.xml + ImageSets/Main/<set>.txt in the layout datasets/voc_eval.py:37-44 reads."""
+    import os
+    base = os.path.join(voc_root, 'VOC2007')
+    os.makedirs(os.path.join(base, 'Annotations'), exist_ok=True)
+    os.makedirs(os.path.join(base, 'ImageSets', 'Main'), exist_ok=True)
+    with open(os.path.join(base, 'ImageSets', 'Main', set_type + '.txt'), 'wt') as f:
+        f.write(''.join(i + '\n' for i in ids))
+    for i, objs in zip(ids, annots):
+        xml = ['<annotation><filename>%s.jpg</filename>' % i]
+        for o in objs:
+            xml.append('<object><name>%s</name><pose>Unspecified</pose><truncated>0</truncated><difficult>%d</difficult>'
+                       '<bndbox><xmin>%d</xmin><ymin>%d</ymin><xmax>%d</xmax><ymax>%d</ymax></bndbox></object>'
+                       % ((o['name'], o['difficult']) + tuple(o['bbox'])))
+        xml.append('</annotation>')
+        with open(os.path.join(base, 'Annotations', i + '.xml'), 'wt') as f:
+            f.write(''.join(xml))

@@ -435,7 +435,58 @@ def gen_np_methods():
     save('np_methods', **out)
 
 
+# --------------------------------------------------------------------------- #
+# datasets/voc_eval.py: result files + the PASCAL VOC evaluator (pure NumPy: the UNMODIFIED reference runs here)
+# --------------------------------------------------------------------------- #
+def gen_voc_eval():
+    import tempfile, types, hashlib, contextlib, io
+    if not hasattr(np, 'bool'):
+        np.bool = bool                              # voc_eval.py:232
+    sys.modules.setdefault('cv2', types.ModuleType('cv2'))     # imported at :16, never used
+    from datasets import voc_eval
+
+    class Dets(np.ndarray):
+        """voc_eval.py:95 tests ``dets == []``, which NumPy 2 refuses to broadcast for a non-empty array."""
+        def __eq__(self, other):
+            return False if isinstance(other, list) else np.ndarray.__eq__(self, other)
+        __hash__ = None
+
+    out = {}
+    seed = 4711
+    ids, annots, all_boxes = synth.make_voc_eval_case(seed, 40)
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_voc_tree(os.path.join(tmp, 'voc'), ids, annots)
+        ev = voc_eval.DetectorEvalPascal(os.path.join(tmp, 'voc'), os.path.join(tmp, 'devkit'), 'test',
+                                         output_dir=os.path.join(tmp, 'output_{}'))
+        boxes = [[(b.view(Dets) if b.shape[0] else []) for b in per_cls] for per_cls in all_boxes]
+        with contextlib.redirect_stdout(io.StringIO()):
+            ev.write_voc_results_file(boxes)
+            files = b''
+            ap07, ap12, npt = [], [], []
+            for ci, cls in enumerate(synth.VOC_CLASSES):
+                fn = ev.get_voc_results_file_template(cls)
+                txt = open(fn, 'rb').read()
+                files += txt
+                if ci == 14:
+                    out['person_file'] = np.frombuffer(txt, np.uint8)
+                cache = os.path.join(tmp, 'cache')
+                rec, prec, a7 = ev.voc_eval(fn, cls, cache, ovthresh=0.5, use_07_metric=True)
+                _, _, a12 = ev.voc_eval(fn, cls, cache, ovthresh=0.5, use_07_metric=False)
+                ap07.append(a7); ap12.append(a12)
+                npt.append(0 if np.isscalar(rec) else rec.shape[0])
+                if ci in (6, 14):
+                    out['rec_%d' % ci], out['prec_%d' % ci] = np.asarray(rec, np.float64), np.asarray(prec, np.float64)
+    out['ap07'], out['ap12'] = np.array(ap07, np.float64), np.array(ap12, np.float64)
+    out['n_dets'] = np.array(npt, np.int64)
+    out['files_sha'] = np.frombuffer(hashlib.sha256(files).digest(), np.uint8)
+    out['cfg'] = np.array([seed, 40], np.int64)
+    save('voc_eval', **out)
+
+
 if __name__ == '__main__':
+    if '--only-voc' in sys.argv:
+        gen_voc_eval()
+        sys.exit(0)
     if '--only-np' in sys.argv:
         gen_np_methods()
         sys.exit(0)
@@ -456,3 +507,4 @@ if __name__ == '__main__':
     gen_tpfp()
     gen_loss_masks()
     gen_np_methods()
+    gen_voc_eval()
