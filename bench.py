@@ -212,30 +212,60 @@ def timed_steps(torch, fn, steps, warmup, flush=None):
     return [a.elapsed_time(b) for a, b in evs]      # ms
 
 
-def pipelined_steps(torch, step, nstreams, steps, warmup):
+def pipelined_steps(torch, step, nstreams, steps, warmup, graph=False):
     """Whole-job time of `steps` back-to-back steps issued round-robin on `nstreams` CUDA streams
     (step k runs on stream k % nstreams with that stream's own outputs / workspaces, so the tail of
     one step overlaps the head of the next): W untimed warm-ups, then events on the current stream
-    around exactly `steps` steps, all streams joined before the end event.  Returns total ms."""
+    around exactly `steps` steps, all streams joined before the end event.  Returns total ms.
+    graph=True: the `steps` launches (same fork / join over the streams) are captured once into a CUDA
+    graph and the timed region is its replay, so the host-side cost of the Python wrapper (~35 us per
+    call, about one batch-64 encode kernel) is not what is measured; falls back to eager issue if the
+    capture fails."""
     from ron_tensorflow_b200 import core
     main = torch.cuda.current_stream()
     streams = [torch.cuda.Stream() for _ in range(nstreams)]
 
-    def issue(k0, k1):
+    def issue(k0, k1, root):
         for s in streams:
-            s.wait_stream(main)
+            s.wait_stream(root)
         for k in range(k0, k1):
             with torch.cuda.stream(streams[k % nstreams]):
                 step(k)
         for s in streams:
-            main.wait_stream(s)
+            root.wait_stream(s)
 
-    issue(0, max(warmup, nstreams))
+    issue(0, max(warmup, nstreams), main)
     torch.cuda.synchronize()
+    g = None
+    pipelined_steps.graphed = False
+    if graph:
+        try:
+            cap = torch.cuda.Stream()
+            cap.wait_stream(main)
+            g = torch.cuda.CUDAGraph()
+            l0 = core.launch_count()
+            with torch.cuda.graph(g, stream=cap):
+                issue(0, steps, torch.cuda.current_stream())
+            launches = core.launch_count() - l0
+            main.wait_stream(cap)
+            g.replay()                                   # one untimed replay
+            torch.cuda.synchronize()
+            pipelined_steps.graphed = True
+        except Exception as e:                           # noqa: BLE001 -- measured eagerly instead
+            sys.stderr.write('bench: CUDA graph capture failed (%s); timing eager launches\n' % e)
+            g = None
+            torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if g is not None:
+        a.record(main)
+        g.replay()
+        b.record(main)
+        torch.cuda.synchronize()
+        pipelined_steps.launches = launches
+        return a.elapsed_time(b)
     l0 = core.launch_count()
     a.record(main)
-    issue(0, steps)
+    issue(0, steps, main)
     b.record(main)
     torch.cuda.synchronize()
     pipelined_steps.launches = core.launch_count() - l0
@@ -306,8 +336,9 @@ def run_ours(args):
         core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, out=outs_pipe[k % 8])
 
     barrier()
-    ms_pipe = pipelined_steps(torch, enc_pipe_step, ENC_STREAMS, args.steps, args.warmup)
+    ms_pipe = pipelined_steps(torch, enc_pipe_step, ENC_STREAMS, args.steps, args.warmup, graph=True)
     enc_launches = pipelined_steps.launches
+    enc_graphed = pipelined_steps.graphed
     barrier()
     del outs_pipe
     t_enc = max_over_ranks(ms_pipe / 1e3)
@@ -398,7 +429,8 @@ def run_ours(args):
             core.tpfp_match(ns, nb, d_gl, d_gb, d_gd, 0.5)
 
         barrier()
-        ms_ppipe = pipelined_steps(torch, post_pipe_step, POST_STREAMS, args.steps, args.warmup)
+        ms_ppipe = pipelined_steps(torch, post_pipe_step, POST_STREAMS, args.steps, args.warmup, graph=True)
+        post_graphed = pipelined_steps.graphed
         post_launches = pipelined_steps.launches
         barrier()
         t_post = max_over_ranks(ms_ppipe / 1e3)
@@ -450,8 +482,8 @@ def run_ours(args):
                                    'select 0.01, clip, min-size 0.03, top-k %d, NMS min-area %.2f keep %d, + VOC TP/FP kernel'
                                    % (POST_B, POST_K, POST_THR, POST_M), 'l2': 'inputs (586 MB) exceed L2',
                        'pipelining': 'value / ms_per_step: steps round-robin on %d CUDA streams (own workspaces and outputs '
-                                     'each); roofline and single_stream_ms_per_step: one stream, events around each step'
-                                     % POST_STREAMS},
+                                     'each)%s; roofline and single_stream_ms_per_step: one stream, events around each step'
+                                     % (POST_STREAMS, ', replayed from one CUDA graph' if post_graphed else ', eager launches')},
             'roofline': {'bound': 'hbm', 'achieved': post_achieved, 'peak': hbm, 'unit': 'GB/s',
                          'frac': post_achieved / hbm, 'traffic': traffic('postprocess_b256'), 'peak_source': peak_src,
                          'note': 'algorithmic 2.29 MB/image over the whole step (init, scatter x2, pivot, top-k, NMS, TP/FP: '
@@ -546,9 +578,10 @@ def run_ours(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD,
                        'pipelining': 'value / ms_per_step: %d steps back to back, round-robin on %d CUDA streams, 8 rotating output '
-                                     'sets (305 MB > L2); roofline: the same step alone on one stream, CUDA events around each '
+                                     'sets (305 MB > L2)%s; roofline: the same step alone on one stream, CUDA events around each '
                                      'launch, L2 flushed between steps (256 MB write): %.4f ms per step'
-                                     % (args.steps, ENC_STREAMS, float(np.mean(ms))),
+                                     % (args.steps, ENC_STREAMS, ', replayed from one CUDA graph' if enc_graphed else ', eager launches',
+                                        float(np.mean(ms))),
                        'l2': 'outputs rotate over 305 MB (> 126 MB L2) in the pipelined run; flushed in the single-stream run'},
             'roofline': {'bound': 'hbm', 'achieved': enc_achieved, 'peak': hbm, 'unit': 'GB/s',
                          'frac': enc_achieved / hbm, 'traffic': traffic('match_encode_b64'), 'peak_source': peak_src,
