@@ -262,6 +262,13 @@ def pipelined_steps(torch, step, nstreams, steps, warmup, graph=False):
         b.record(main)
         torch.cuda.synchronize()
         pipelined_steps.launches = launches
+        if os.environ.get('RONK_BENCH_VERBOSE'):           # spread of further replays, diagnostics only
+            extra = []
+            for _ in range(5):
+                c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c.record(main); g.replay(); d.record(main); torch.cuda.synchronize()
+                extra.append(c.elapsed_time(d))
+            sys.stderr.write('bench: timed replay %.4f ms, further replays %s\n' % (a.elapsed_time(b), ['%.4f' % v for v in extra]))
         return a.elapsed_time(b)
     l0 = core.launch_count()
     a.record(main)
@@ -270,6 +277,23 @@ def pipelined_steps(torch, step, nstreams, steps, warmup, graph=False):
     torch.cuda.synchronize()
     pipelined_steps.launches = core.launch_count() - l0
     return a.elapsed_time(b)
+
+
+def rank_gt_batch(synth, config, batch, g_lo, g_hi, rank):
+    """Weak scaling with the same work on every GPU: rank r gets its own images (seeds of images
+    [r * batch, (r + 1) * batch)) but with the ground-truth COUNTS of rank 0's batch, image by image --
+    the cost of an image is proportional to its count (1..50), and independent draws would make the
+    slowest rank's batch up to ~10 % heavier than rank 0's."""
+    boxes, labels, counts = synth.make_gt_batch(config, batch, g_lo, g_hi)
+    if rank == 0:
+        return boxes, labels, counts
+    boxes = np.zeros_like(boxes)
+    labels = np.zeros_like(labels)
+    for b in range(batch):
+        bx, lb = synth.make_gt(synth.image_seed(config, rank * batch + b), int(counts[b]))
+        boxes[b, :counts[b]] = bx
+        labels[b, :counts[b]] = lb
+    return boxes, labels, counts
 
 
 def run_ours(args):
@@ -306,10 +330,11 @@ def run_ours(args):
     anchors = net.anchors(net.params.img_shape)
     aset = anchors.anchor_set
     N = aset.N
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    # > 126 MB L2, and long enough (~80 us of device time) for the host to have the next launch queued behind it
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     # ---------------------------------------------------------------- stage A: match + encode
-    boxes, labels, counts = synth.make_gt_batch(2, ENC_B, ENC_G[0], ENC_G[1], first_image=rank * ENC_B)
+    boxes, labels, counts = rank_gt_batch(synth, 2, ENC_B, ENC_G[0], ENC_G[1], rank)
     d_boxes = torch.from_numpy(boxes).to(dev)
     d_labels = torch.from_numpy(labels).to(dev)
     d_counts = torch.from_numpy(counts).to(dev)
@@ -349,7 +374,7 @@ def run_ours(args):
     # same path at batch 256 (the size the north-star roofline target is quoted on); outputs of
     # one step (152 MB) exceed L2, and 4 output sets rotate so nothing is L2 resident across steps
     B2 = 256
-    boxes2, labels2, counts2 = synth.make_gt_batch(2, B2, ENC_G[0], ENC_G[1], first_image=rank * B2)
+    boxes2, labels2, counts2 = rank_gt_batch(synth, 2, B2, ENC_G[0], ENC_G[1], rank)
     d2 = [torch.from_numpy(x).to(dev) for x in (boxes2, labels2, counts2)]
     outs2 = [new_out(B2) for _ in range(4)]
     it2 = [0]
@@ -579,7 +604,7 @@ def run_ours(args):
             'config': {'workload': WORKLOAD,
                        'pipelining': 'value / ms_per_step: %d steps back to back, round-robin on %d CUDA streams, 8 rotating output '
                                      'sets (305 MB > L2)%s; roofline: the same step alone on one stream, CUDA events around each '
-                                     'launch, L2 flushed between steps (256 MB write): %.4f ms per step'
+                                     'launch, L2 flushed between steps (512 MB write): %.4f ms per step'
                                      % (args.steps, ENC_STREAMS, ', replayed from one CUDA graph' if enc_graphed else ', eager launches',
                                         float(np.mean(ms))),
                        'l2': 'outputs rotate over 305 MB (> 126 MB L2) in the pipelined run; flushed in the single-stream run'},
