@@ -29,7 +29,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENC_B, ENC_G = 64, (1, 50)
-ENC_STREAMS, POST_STREAMS = 2, 3      # steps are issued round-robin on this many CUDA streams for `value`
+ENC_STREAMS = int(os.environ.get("RONK_BENCH_ENC_STREAMS", "2"))      # steps are issued round-robin on this many CUDA streams for `value`
+POST_STREAMS = int(os.environ.get("RONK_BENCH_POST_STREAMS", "3"))
 WORKLOAD = ('BASELINE configs[1]: RON-320 joint match+encode over all 4 layers (21250 anchors), batch 64 per GPU, '
             '1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels')
 POST_B, POST_K, POST_M, POST_THR = 256, 400, 200, 0.45
