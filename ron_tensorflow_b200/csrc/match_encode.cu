@@ -237,7 +237,7 @@ __device__ __forceinline__ unsigned long long trace_now() {
 #endif
 
 constexpr int kEncThreads = 128;
-constexpr int kEncPrefetch = 4;     // flat anchors per thread whose compact index is fetched before the sweep
+constexpr int kEncPrefetch = 3;     // flat anchors per thread whose compact index is fetched before the sweep
 
 // One work item: SETS sets of 64 inside anchors starting at compact index c0, GT list cut in SPLIT
 // parts (SETS * SPLIT = 4 warps); writes the outputs of the flat anchors [n_lo, n_hi).
@@ -253,6 +253,8 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
     float* s_area = reinterpret_cast<float*>(s_lab + p.gcap);     // [gcap]
     __shared__ float s_mv[SPLIT][kTile];                          // per-anchor max overlap, per GT part
     __shared__ int s_mg[SPLIT][kTile];                            // per-anchor first argmax (-1: none)
+    __shared__ int s_pn[kTile], s_pg[kTile];                      // anchors matched by threshold: flat index, GT
+    __shared__ unsigned s_npos;
     __shared__ int s_last;
 
     const unsigned full = 0xffffffffu;
@@ -265,6 +267,7 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
     // slot of each thread (before the GT count is known), the image-wide bests, this lane's anchors and
     // the compact indices of the first flat anchors it will write.  One global round trip instead of
     // four on the critical path of every CTA.
+    if (tid == 0) s_npos = 0u;                                    // ordered before its first use by the barriers below
     const bool spec = tid < p.Gmax;
     const float4 v_spec = spec ? gtb[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
     const long long l_spec = spec ? gtl[tid] : 0ll;
@@ -348,8 +351,10 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
         if (v > s_init[g]) atomicMax(p.ws_keys + (size_t)b * p.Gmax + g, v);
     }
 
-    // ---- label + encode + store the item's flat anchor range (forced anchors are rewritten
-    // by the CTA that finishes the image last)
+    // ---- label + store the item's flat anchor range (forced anchors are rewritten by the CTA that
+    // finishes the image last).  Anchors matched by threshold are only listed here: their encoding (~300
+    // dependent instructions: 4 IEEE divisions, 2 double-precision logs) runs after the loop, one listed
+    // anchor per thread, instead of once per warp iteration that happens to hold one or two of them.
     int q = 0;
     for (int n = n_lo + tid; n < n_hi; n += kEncThreads, ++q) {
         int c;
@@ -357,7 +362,6 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
             case 0: c = cpre[0]; break;
             case 1: c = cpre[1]; break;
             case 2: c = cpre[2]; break;
-            case 3: c = cpre[3]; break;
             default: c = p.cidx[n]; break;
         }
         float mv = 0.f;
@@ -379,20 +383,27 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
         int mi = ign ? -2 : (neg ? -1 : a2g);
         if (G == 0) mi = -1;
         long long label = 0;
-        float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (mi >= 0) {
             label = s_lab[a2g];
-            loc = encode_loc(s_box[a2g], p.enc[n], p);
+            const unsigned slot = atomicAdd(&s_npos, 1u);        // <= kTile: only inside anchors can match
+            s_pn[slot] = n;
+            s_pg[slot] = a2g;
             if (!p.gt_max_first) atomicOr(p.ws_claimed + (size_t)b * p.Gmax + a2g, 1u);
         } else if (mi < -1) {
             label = -1;
         }
         size_t o = (size_t)b * p.N + n;
         p.out_labels[o] = label;
-        p.out_loc[o] = loc;
+        if (mi < 0) p.out_loc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
         p.out_scores[o] = mv;
         if (p.out_matched) p.out_matched[o] = mi;
         if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
+    }
+
+    __syncthreads();
+    for (unsigned k = tid; k < s_npos; k += kEncThreads) {
+        const int n = s_pn[k];
+        p.out_loc[(size_t)b * p.N + n] = encode_loc(s_box[s_pg[k]], p.enc[n], p);
     }
 
     // ---- publish; the last item of the image applies the per-GT forcing.  Barrier first, then
