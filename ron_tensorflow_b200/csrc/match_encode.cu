@@ -19,7 +19,8 @@
 //      two GT boxes per iteration, keeps the per-anchor (max, first argmax) in registers and the
 //      per-GT (max, lowest anchor) as a packed u64 in shared memory -- the REDUX + atomicMax
 //      path only runs when a lane can reach the current per-GT best;
-//   3. labels, encodes and stores labels / loc / scores for its flat anchor range;
+//   3. labels and stores labels / scores for its flat anchor range; anchors matched by threshold are
+//      listed in shared memory and their localisations encoded afterwards, one listed anchor per thread;
 //   4. publishes its per-GT bests with one global atomicMax each and bumps the image's tile
 //      counter; the CTA that finishes an image LAST applies "lowest GT index claims the anchor"
 //      (tf.argmax of the one-hot mask, ssd_common.py:74-75), rewrites those (<= G) anchors and

@@ -12,7 +12,7 @@ try:
     d = json.load(open('gpurun_out/${tag}_bench.json'))
     print('encode b64  %.1f us  frac %.3f  e2e %.0f img/s' % (d['ms_per_step']*1e3, d['roofline']['frac'], d['e2e']['value']))
     s = d['stages']
-    print('encode b256 %.1f us  frac %.3f' % (s['encode_b256']['ms_per_step']*1e3, s['encode_b256']['roofline']['frac']))
+    print('encode b256 %.1f us (single %.1f)  frac %.3f' % (s['encode_b256']['ms_per_step']*1e3, s['encode_b256'].get('single_stream_ms_per_step', 0)*1e3, s['encode_b256']['roofline']['frac']))
     if s.get('postprocess'):
         print('post b256   %.1f us  frac %.3f  e2e %.0f img/s' % (s['postprocess']['ms_per_step']*1e3, s['postprocess']['roofline']['frac'], s['postprocess']['e2e']['value']))
     print('cpu', d.get('cpu_baseline'))
