@@ -21,6 +21,7 @@ runtime's own kernels.  Each op below states the TF semantics it restates:
 
 It is not a general TensorFlow replacement and never ships with the product.
 """
+import os
 import sys
 import types
 import importlib.abc
@@ -666,6 +667,123 @@ def _top_k(x, k=1, sorted=True, name=None):
 
 
 # --------------------------------------------------------------------------- #
+# tf.train.Example / tf.python_io.TFRecordWriter / tf.gfile: enough for the reference's
+# datasets/pascalvoc_to_tfrecords.py to run unmodified and write real TFRecord files
+# (public formats: protobuf wire encoding of Example, TFRecord framing with masked CRC-32C)
+# --------------------------------------------------------------------------- #
+def _pb_varint(v):
+    v &= (1 << 64) - 1
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _pb_len(field, payload):
+    return _pb_varint((field << 3) | 2) + _pb_varint(len(payload)) + payload
+
+
+class _PbList(object):
+    def __init__(self, value=()):
+        self.value = list(value)
+
+
+class BytesList(_PbList):
+    def SerializeToString(self):
+        return b''.join(_pb_len(1, bytes(v)) for v in self.value)
+
+
+class FloatList(_PbList):
+    def SerializeToString(self):          # repeated float value = 1 [packed = true]
+        return _pb_len(1, np.asarray(self.value, '<f4').tobytes()) if self.value else b''
+
+
+class Int64List(_PbList):
+    def SerializeToString(self):          # repeated int64 value = 1 [packed = true]
+        return _pb_len(1, b''.join(_pb_varint(int(v)) for v in self.value)) if self.value else b''
+
+
+class Feature(object):
+    def __init__(self, bytes_list=None, float_list=None, int64_list=None):
+        self.bytes_list, self.float_list, self.int64_list = bytes_list, float_list, int64_list
+
+    def SerializeToString(self):
+        for field, v in ((1, self.bytes_list), (2, self.float_list), (3, self.int64_list)):
+            if v is not None:
+                return _pb_len(field, v.SerializeToString())
+        return b''
+
+
+class Features(object):
+    def __init__(self, feature=None):
+        self.feature = dict(feature or {})
+
+    def SerializeToString(self):          # map<string, Feature> feature = 1; deterministic: sorted by key
+        out = b''
+        for k in sorted(self.feature):
+            out += _pb_len(1, _pb_len(1, k.encode('utf-8')) + _pb_len(2, self.feature[k].SerializeToString()))
+        return out
+
+
+class Example(object):
+    def __init__(self, features=None):
+        self.features = features
+
+    def SerializeToString(self):
+        return _pb_len(1, self.features.SerializeToString())
+
+
+def _crc32c(data):
+    c = 0xffffffff
+    for b in data:
+        c ^= b
+        for _ in _b.range(8):
+            c = (c >> 1) ^ (0x82f63b78 if c & 1 else 0)
+    return c ^ 0xffffffff
+
+
+def _masked_crc(data):
+    c = _crc32c(data)
+    return (((c >> 15) | (c << 17)) + 0xa282ead8) & 0xffffffff
+
+
+class _TFRecordWriter(object):
+    def __init__(self, path, options=None):
+        self._f = open(path, 'wb')
+
+    def write(self, record):
+        import struct
+        head = struct.pack('<Q', len(record))
+        self._f.write(head + struct.pack('<I', _masked_crc(head)) + record + struct.pack('<I', _masked_crc(record)))
+
+    def close(self):
+        self._f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+
+class _FastGFile(object):
+    def __init__(self, name, mode='r'):
+        self._f = open(name, mode)
+
+    def read(self, n=-1):
+        return self._f.read(n)
+
+    def close(self):
+        self._f.close()
+
+
+# --------------------------------------------------------------------------- #
 # permissive stubs for everything else (slim, contrib, flags, ...)
 # --------------------------------------------------------------------------- #
 class _Stub(object):
@@ -743,7 +861,15 @@ contrib = _Stub('tensorflow.contrib')
 app = _Stub('tensorflow.app')
 logging = _Stub('tensorflow.logging')
 summary = _Stub('tensorflow.summary')
-train = _Stub('tensorflow.train')
+train = _StubModule('tensorflow.train')
+train.Example, train.Features, train.Feature = Example, Features, Feature
+train.BytesList, train.FloatList, train.Int64List = BytesList, FloatList, Int64List
+python_io = _StubModule('tensorflow.python_io')
+python_io.TFRecordWriter = _TFRecordWriter
+gfile = _StubModule('tensorflow.gfile')
+gfile.FastGFile = _FastGFile
+gfile.Exists = os.path.exists
+gfile.MakeDirs = lambda p: os.makedirs(p, exist_ok=True)
 image = _Stub('tensorflow.image')
 layers = _Stub('tensorflow.layers')
 GraphKeys = _Stub('tensorflow.GraphKeys')

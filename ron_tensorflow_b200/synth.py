@@ -150,8 +150,10 @@ def make_voc_eval_case(seed, n_images=40, width=500, height=375):
     return ids, annots, all_boxes
 
 
-def write_voc_tree(voc_root, ids, annots, set_type='test'):
-    """Annotations/*.xml + ImageSets/Main/<set>.txt in the layout datasets/voc_eval.py:37-44 reads."""
+def write_voc_tree(voc_root, ids, annots, set_type='test', with_size=None, with_images=False):
+    """Annotations/*.xml + ImageSets/Main/<set>.txt in the layout datasets/voc_eval.py:37-44 reads; with_size =
+    (height, width, depth) adds the <size> element and with_images tiny stand-in JPEGImages/*.jpg files, which
+    datasets/pascalvoc_to_tfrecords.py needs."""
     import os
     base = os.path.join(voc_root, 'VOC2007')
     os.makedirs(os.path.join(base, 'Annotations'), exist_ok=True)
@@ -160,6 +162,12 @@ def write_voc_tree(voc_root, ids, annots, set_type='test'):
         f.write(''.join(i + '\n' for i in ids))
     for i, objs in zip(ids, annots):
         xml = ['<annotation><filename>%s.jpg</filename>' % i]
+        if with_size:
+            xml.append('<size><width>%d</width><height>%d</height><depth>%d</depth></size>' % (with_size[1], with_size[0], with_size[2]))
+        if with_images:
+            os.makedirs(os.path.join(base, 'JPEGImages'), exist_ok=True)
+            with open(os.path.join(base, 'JPEGImages', i + '.jpg'), 'wb') as f:
+                f.write(b'\xff\xd8 synthetic ' + i.encode('ascii') + b' \xff\xd9')
         for o in objs:
             xml.append('<object><name>%s</name><pose>Unspecified</pose><truncated>0</truncated><difficult>%d</difficult>'
                        '<bndbox><xmin>%d</xmin><ymin>%d</ymin><xmax>%d</xmax><ymax>%d</ymax></bndbox></object>'

@@ -483,7 +483,29 @@ def gen_voc_eval():
     save('voc_eval', **out)
 
 
+# --------------------------------------------------------------------------- #
+# datasets/pascalvoc_to_tfrecords.py: the reference's own converter writes a TFRecord file through the shim's
+# tf.train.Example / tf.python_io.TFRecordWriter (public wire formats); committed as a fixture for the reader
+# --------------------------------------------------------------------------- #
+def gen_tfrecord():
+    import tempfile, contextlib, io, shutil
+    from datasets import pascalvoc_to_tfrecords as conv
+    seed, n = 515, 12
+    ids, annots, _ = synth.make_voc_eval_case(seed, n)
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, 'VOC2007') + os.sep
+        synth.write_voc_tree(tmp, ids, annots, with_size=(375, 500, 3), with_images=True)
+        os.makedirs(os.path.join(tmp, 'out'))
+        with contextlib.redirect_stdout(io.StringIO()):
+            conv.run(src, os.path.join(tmp, 'out'), name='voc_synth', shuffling=False)
+        shutil.copy(os.path.join(tmp, 'out', 'voc_synth_000.tfrecord'), os.path.join(HERE, 'voc_synth_000.tfrecord'))
+    print('%-30s %8.1f KB' % ('voc_synth_000.tfrecord', os.path.getsize(os.path.join(HERE, 'voc_synth_000.tfrecord')) / 1024.))
+
+
 if __name__ == '__main__':
+    if '--only-tfrecord' in sys.argv:
+        gen_tfrecord()
+        sys.exit(0)
     if '--only-voc' in sys.argv:
         gen_voc_eval()
         sys.exit(0)
@@ -508,3 +530,4 @@ if __name__ == '__main__':
     gen_loss_masks()
     gen_np_methods()
     gen_voc_eval()
+    gen_tfrecord()
