@@ -227,10 +227,10 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         const size_t row = (size_t)t.b * t.n_l + t.t0;
         tma_load_1d(base + stage_floats * 4, reinterpret_cast<const float4*>(p.loc[t.layer]) + row, row_bytes, &s_bar[st]);
     };
-    auto load_gate = [&](const TileInfo& t) -> bool {
-        bool gate = tid < t.rows;
-        if (gate && p.has_obj) gate = p.obj[t.layer][(size_t)t.b * t.n_l + t.t0 + tid] > p.obj_thr;
-        return gate;
+    // objectness of this thread's row: only the LOAD is issued here (a tile ahead); the comparison waits until
+    // the value is needed, so the load's latency is hidden behind the current tile's work
+    auto load_obj = [&](const TileInfo& t) -> float {
+        return (p.has_obj && tid < t.rows) ? p.obj[t.layer][(size_t)t.b * t.n_l + t.t0 + tid] : 0.f;
     };
 
     // tiles are visited grid-stride; (b, r) = (image, tile inside the image) advances without divisions
@@ -240,7 +240,7 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
     if (b >= p.B) return;
     TileInfo t = tile_info(p, b, p.r_lo + r);
     if (tid == 0) issue(t, 0);
-    bool gate = load_gate(t);
+    float objv = load_obj(t);
     unsigned phase = 0u;   // bit st = parity the next wait on stage st must see
     for (int it = 0; b < p.B; ++it) {
         const int st = it & 1;
@@ -248,12 +248,13 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         int nb = b + step_b, nr = r + step_r;
         if (nr >= cnt) { nr -= cnt; ++nb; }
         TileInfo tn = t;
-        bool gate_next = false;
+        float objv_next = 0.f;
         if (nb < p.B) {
             tn = tile_info(p, nb, p.r_lo + nr);
             if (tid == 0) issue(tn, st ^ 1);
-            gate_next = load_gate(tn);          // objectness of the next tile: the load overlaps this tile's work
+            objv_next = load_obj(tn);           // objectness of the next tile: the load overlaps this tile's work
         }
+        const bool gate = tid < t.rows && (!p.has_obj || objv > p.obj_thr);
 
         // ---- A. objectness gate + compaction of the surviving rows
         const unsigned gmask = __ballot_sync(full, gate);
@@ -311,7 +312,7 @@ scatter_candidates_kernel(const __grid_constant__ PostParams p) {
         t = tn;
         b = nb;
         r = nr;
-        gate = gate_next;
+        objv = objv_next;
     }
 }
 
