@@ -18,6 +18,11 @@
 namespace ronk {
 
 constexpr int kNmsWarps = 4;
+constexpr int kNmsPad = 8;            // kept boxes are tested in unrolled groups of this many
+
+__host__ __device__ constexpr int nms_smem_per_warp(int M) {
+    return ((M + kNmsPad + 32) * 20 + M * 4 + 15) & ~15;
+}
 
 struct NmsParams {
     const float* scores;
@@ -58,13 +63,21 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.x * kNmsWarps + warp;
     if (seg >= p.S) return;
-    const int per_warp = ((p.M + 32) * 20 + p.M * 4 + 15) & ~15;   // float4 + float for M kept and 32 chunk entries, + thr * vol
+    // per warp: float4 + float for M kept (+ kNmsPad sentinels) and 32 chunk entries, + thr * vol
+    const int per_warp = nms_smem_per_warp(p.M);
     unsigned char* base = smem + (size_t)warp * per_warp;
     float4* s_kbox = reinterpret_cast<float4*>(base);
-    float4* s_cbox = s_kbox + p.M;
+    float4* s_cbox = s_kbox + p.M + kNmsPad;
     float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
     float* s_cvol = s_kvol + p.M;
     float* s_kt = s_cvol + 32;            // thr * vol of the kept boxes (+inf for empty boxes: they suppress nothing)
+    // Sentinels behind the kept list: a box no candidate intersects, with threshold +inf.  The fast loop below
+    // then always runs whole groups of kNmsPad kept boxes, fully unrolled, without a bound inside the group.
+    for (int i = lane; i < p.M + kNmsPad; i += 32) {
+        s_kbox[i] = make_float4(2.f, 2.f, -1.f, -1.f);
+        s_kt[i] = __int_as_float(0x7f800000);
+    }
+    __syncwarp();
     // fast 'min' loop: valid while thr > 0 and every box seen so far has all corners in [0, 1]
     bool unit = (p.mode == RONK_NMS_MIN) && (p.thr > 0.f);
 
@@ -96,10 +109,9 @@ nms_kernel(const __grid_constant__ NmsParams p) {
             // which the exact division must decide is taken against thr vol_j >= min(.): conservative.
             const float tj = p.thr * vol;
             const float tolj = tj * 1e-6f;
-            for (int i0 = 0; i0 < count; i0 += 8) {
-                const int lim = min(8, count - i0);
-#pragma unroll 4
-                for (int i = 0; i < lim; ++i) {
+            for (int i0 = 0; i0 < count; i0 += kNmsPad) {
+#pragma unroll
+                for (int i = 0; i < kNmsPad; ++i) {                 // entries past `count` are sentinels: d = -tj
                     const float4 kb = s_kbox[i0 + i];
                     const float kt = s_kt[i0 + i];
                     const float h = __saturatef(fminf(box.z, kb.z) - fmaxf(box.x, kb.x));
@@ -234,7 +246,7 @@ extern "C" int ronk_nms_batch(const float* scores, const float* boxes, int S, in
         RONK_LAUNCHED();
         p.order = (const int*)ws;
     }
-    size_t smem = (size_t)kNmsWarps * ((((size_t)keep_top_k + 32) * 20 + (size_t)keep_top_k * 4 + 15) & ~(size_t)15);
+    size_t smem = (size_t)kNmsWarps * (size_t)nms_smem_per_warp(keep_top_k);
     if (smem > 48 * 1024)
         RONK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_kernel<<<(S + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, smem, st>>>(p);
