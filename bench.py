@@ -280,6 +280,26 @@ def pipelined_steps(torch, step, nstreams, steps, warmup, graph=False):
     return a.elapsed_time(b)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, before any pinned host buffer is
+    allocated: the host<->device copies of the e2e legs then stay on the GPU's own socket (one process per
+    GPU; without it the ranks of a box share one socket's memory bandwidth).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception as e:                                   # noqa: BLE001
+        sys.stderr.write('bench: NUMA binding skipped (%s)\n' % e)
+        return 0
+
+
 def rank_gt_batch(synth, config, batch, g_lo, g_hi, rank):
     """Weak scaling with the same work on every GPU: rank r gets its own images (seeds of images
     [r * batch, (r + 1) * batch)) but with the ground-truth COUNTS of rank 0's batch, image by image --
@@ -311,6 +331,7 @@ def run_ours(args):
         raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     hbm, peak_src = peaks()
