@@ -312,6 +312,18 @@ int ronk_voc_match(const double* det_boxes, const int32_t* det_offsets, const do
                    const int32_t* gt_offsets, const uint8_t* gt_difficult, int n_images, int max_gt,
                    double ovthresh, uint8_t* out_tp, uint8_t* out_fp, void* stream);
 
+/* ------------------------------------------- host-buffer path of match + encode (sparse device -> host transfer)
+ * 16 of the 28 target bytes per anchor are the localisation row, non-zero for ~1 % of the anchors:
+ * ronk_sparse_rows_pack packs the non-zero rows of a device tensor rows [T,4] (T = B*N) into a fixed-capacity packet
+ * {header int32[4] = (n, 0, 0, 0); row indices int32[cap]; pad to 16 B; rows float4[cap]} of
+ * ronk_sparse_rows_packet_bytes(cap) bytes.  After the packet has been copied to the host, ronk_host_rows_apply
+ * (plain host code) zeroes the rows the PREVIOUS packet of the same host array wrote (or pass NULL) and writes the new
+ * ones; the array must be zero elsewhere.  Returns 1, touching nothing, when the packet overflowed (n > cap): copy
+ * the dense tensor instead and zero the array before the next sparse step.  Labels and scores are copied dense. */
+size_t ronk_sparse_rows_packet_bytes(int cap);
+int ronk_sparse_rows_pack(const float* rows, long long T, int cap, void* packet_dev, void* stream);
+int ronk_host_rows_apply(const void* packet_host, const void* prev_packet_host, int cap, float* rows_host);
+
 /* number of kernel launches issued by this library in this process since load
  * (bench.py reports it as gpu_launches) */
 long long ronk_launch_count(void);

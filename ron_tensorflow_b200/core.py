@@ -738,6 +738,97 @@ def localization_loss(localisations, glocalisations, cls_positive_mask, sigma=3.
     return out[0]
 
 
+# ----------------------------------------------------------------------------- host-buffer encode (sparse D2H)
+def host_rows_apply(packet, prev_packet, cap, rows_host):
+    """Host side of the sparse transfer (ronk_host_rows_apply): packet / prev_packet are CPU uint8 tensors (or
+    None), rows_host a float32 CPU tensor [T,4].  Returns False when the packet overflowed."""
+    rc = _ffi.lib().ronk_host_rows_apply(ctypes.c_void_p(packet.data_ptr()),
+                                         ctypes.c_void_p(prev_packet.data_ptr()) if prev_packet is not None else None,
+                                         int(cap), ctypes.c_void_p(rows_host.data_ptr()))
+    if rc == 1:
+        return False
+    _ffi.check(rc)
+    return True
+
+
+class HostEncoder(object):
+    """match + encode for callers whose ground truth and targets live in HOST memory (the reference encodes on
+    the CPU inside its input pipeline).  ``submit(slot, boxes, labels, counts)`` copies the pinned ground truth of
+    one batch to the device, runs the encode kernel and starts the device->host transfer on the slot's stream;
+    ``collect(slot)`` waits for it and returns the slot's pinned host tensors dict(labels [B,N] int64, loc [B,N,4],
+    scores [B,N]) -- valid until the slot is submitted again.  Two or more slots overlap the transfers of one
+    batch with the kernel of the next.  Labels and scores are copied dense; the localisations (16 of the 28 bytes
+    per anchor, non-zero for ~1 % of the anchors) travel as a packet of their non-zero rows (ronk_sparse_rows_pack)
+    applied to a host array that is kept zero elsewhere; a batch whose packet overflows falls back to a dense copy."""
+
+    def __init__(self, anchors, batch, g_max, slots=2, positive_threshold=0.5, ignore_threshold=0.3, prior_scaling=_PS,
+                 loc_fraction=0.05):
+        _require_cuda()
+        self.anchors, self.B, self.G = anchors, int(batch), int(g_max)
+        self.args = (float(positive_threshold), float(ignore_threshold), prior_scaling)
+        dev, N = anchors.device, anchors.N
+        T = self.B * N
+        self.cap = max(int(T * loc_fraction), 32)
+        self.packet_bytes = int(_ffi.lib().ronk_sparse_rows_packet_bytes(self.cap))
+        self.slots = []
+        for _ in range(int(slots)):
+            s = dict(stream=torch.cuda.Stream(device=dev), event=torch.cuda.Event(),
+                     d_in=(torch.empty((self.B, self.G, 4), dtype=torch.float32, device=dev),
+                           torch.empty((self.B, self.G), dtype=torch.int64, device=dev),
+                           torch.empty((self.B,), dtype=torch.int32, device=dev)),
+                     d_out=dict(labels=torch.empty((self.B, N), dtype=torch.int64, device=dev),
+                                loc=torch.empty((self.B, N, 4), dtype=torch.float32, device=dev),
+                                scores=torch.empty((self.B, N), dtype=torch.float32, device=dev)),
+                     d_packet=torch.empty((self.packet_bytes,), dtype=torch.uint8, device=dev),
+                     h_packet=[torch.empty((self.packet_bytes,), dtype=torch.uint8).pin_memory() for _ in range(2)],
+                     h_out=dict(labels=torch.empty((self.B, N), dtype=torch.int64).pin_memory(),
+                                loc=torch.zeros((self.B, N, 4), dtype=torch.float32).pin_memory(),
+                                scores=torch.empty((self.B, N), dtype=torch.float32).pin_memory()),
+                     parity=0, has_prev=False, dirty=False, busy=False)
+            self.slots.append(s)
+        self.d2h_bytes_per_step = self.packet_bytes + T * (8 + 4)
+
+    def submit(self, slot, gt_boxes, gt_labels, gt_counts):
+        """gt_* : pinned CPU tensors (or NumPy arrays) of shapes [B,Gmax,4] / [B,Gmax] / [B]."""
+        s = self.slots[slot]
+        s['stream'].wait_stream(torch.cuda.current_stream(self.anchors.device))
+        with torch.cuda.stream(s['stream']):
+            for dst, src in zip(s['d_in'], (gt_boxes, gt_labels, gt_counts)):
+                dst.copy_(src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
+            match_encode(self.anchors, s['d_in'][0], s['d_in'][1], s['d_in'][2], self.args[0], self.args[1], self.args[2],
+                         out=s['d_out'])
+            with torch.cuda.device(self.anchors.device):
+                _ffi.check(_ffi.lib().ronk_sparse_rows_pack(_ptr(s['d_out']['loc']), self.B * self.anchors.N, self.cap,
+                                                            _ptr(s['d_packet']), _stream()))
+            s['h_packet'][s['parity']].copy_(s['d_packet'], non_blocking=True)
+            s['h_out']['labels'].copy_(s['d_out']['labels'], non_blocking=True)
+            s['h_out']['scores'].copy_(s['d_out']['scores'], non_blocking=True)
+            s['event'].record()
+        s['busy'] = True
+
+    def collect(self, slot):
+        s = self.slots[slot]
+        if not s['busy']:
+            raise RuntimeError('HostEncoder.collect: nothing was submitted on this slot')
+        s['event'].synchronize()
+        s['busy'] = False
+        h = s['h_out']
+        if s['dirty']:                                   # the last batch of this slot came back dense
+            h['loc'].zero_()
+            s['dirty'], s['has_prev'] = False, False
+        ok = host_rows_apply(s['h_packet'][s['parity']], s['h_packet'][s['parity'] ^ 1] if s['has_prev'] else None,
+                             self.cap, h['loc'])
+        if ok:
+            s['has_prev'] = True
+            s['parity'] ^= 1
+        else:                                            # packet overflow: dense copy for this batch
+            with torch.cuda.stream(s['stream']):
+                h['loc'].copy_(s['d_out']['loc'], non_blocking=True)
+            s['stream'].synchronize()
+            s['dirty'], s['has_prev'] = True, False
+        return h
+
+
 # ----------------------------------------------------------------------------- CUDA graphs
 class Graphed(object):
     """Capture one call of ``fn(*args)`` (any function of this package: every libronk entry point is

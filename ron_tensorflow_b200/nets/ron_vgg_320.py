@@ -117,6 +117,12 @@ class RONNet(object):
                                  ignore_threshold, self.params.prior_scaling, want_matched=want_matched,
                                  want_objness=want_objness)
 
+    def host_encoder(self, batch, g_max, anchors=None, slots=2, positive_threshold=0.5, ignore_threshold=0.3, **kw):
+        """Batched encode for ground truth and targets in HOST memory (the reference encodes on the CPU inside its
+        input pipeline): see core.HostEncoder -- submit(slot, boxes, labels, counts) / collect(slot)."""
+        return core.HostEncoder(self._resolve(anchors), batch, g_max, slots, positive_threshold, ignore_threshold,
+                                self.params.prior_scaling, **kw)
+
     # ------------------------------------------------------------------- decode
     def bboxes_decode(self, feat_localizations, anchors, scope='ssd_bboxes_decode'):
         """reference: nets/ron_vgg_320.py:188-195."""
