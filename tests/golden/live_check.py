@@ -97,6 +97,24 @@ def main():
             bb = np_methods.ssd_bboxes_select_layer(pred[None], pb[None], None, select_threshold=sel, decode=False)
             for x, y, w in zip(a, bb, ('classes', 'scores', 'boxes')):
                 same(x, y, 'np_methods select ' + w)
+    # ---- the eval post-process chain of eval_ron_network.py:226-236 on one image (RONNet.detected_bboxes), once per run
+    from ron_tensorflow_b200 import synth
+    p = net.params
+    layer_sizes = [a[0].shape[0] * a[0].shape[1] * a[2].shape[0] for a in anchors]
+    apc = [a[2].shape[0] for a in anchors]
+    hot = int(rng.integers(20, 200))
+    loc, pred, obj = synth.make_predictions(int(rng.integers(1, 1 << 30)), 1, sum(layer_sizes), p.num_classes, hot=hot)
+    split = lambda x: [T(t) for t in synth.split_layers(x, layer_sizes, p.feat_shapes, apc)]
+    dec = net.bboxes_decode(split(loc), anchors)
+    filt = [tf.cast(tf.greater(o, 0.03), tf.float32) * pr for o, pr in zip(split(obj[..., None]), split(pred))]
+    K, M, thr = int(rng.integers(20, 80)), int(rng.integers(5, 40)), float(rng.uniform(0.3, 0.6))
+    rs, rb = net.detected_bboxes(filt, dec, select_threshold=0.01, nms_threshold=thr, clipping_bbox=[0., 0., 1., 1.],
+                                 top_k=K, keep_top_k=M)
+    mine = O.detected_bboxes_image(pred[0], loc[0], O.flat_decode_anchors(O.anchors_all_layers(O.RON320)), obj[0], 0.03,
+                                   0.01, thr, [0., 0., 1., 1.], K, M)
+    classes = sorted(rs.keys())
+    same(mine['scores'], np.stack([npy(rs[c])[0] for c in classes]), 'detected_bboxes scores')
+    same(mine['boxes'], np.stack([npy(rb[c])[0] for c in classes]), 'detected_bboxes boxes')
     print('live check ok: seed %d, %d cases' % (seed, cases))
 
 
