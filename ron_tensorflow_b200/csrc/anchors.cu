@@ -6,7 +6,9 @@
 #include <math_constants.h>
 #include <string.h>
 
-#include "common.cuh"
+#include <algorithm>
+
+#include "encode_common.cuh"
 
 namespace ronk {
 
@@ -73,6 +75,177 @@ anchor_flat_kernel(const float4* __restrict__ yxhw, const int* __restrict__ bord
     inside[n] = in ? 1 : 0;
 }
 
+// Row / column tables, inside rectangles and work items of the grid kernel (match_encode_grid.cu).  Every property the
+// kernel relies on is CHECKED here against the per-anchor tables the generator kernel produced: corners separable bit for
+// bit, both corner sequences monotone, inside mask = rows x columns, both contiguous.  Any failure leaves grid_ok = 0.
+static cudaError_t build_grid(ronk_anchors* h, const std::vector<float>& cor, const std::vector<uint8_t>& in,
+                              const std::vector<int>& idx) {
+    h->grid_ok = 0;
+    if (h->kind < 0) return cudaSuccess;
+    const LayerTable& t = h->tab;
+    auto bits = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+    std::vector<float> rowtab, coltab;
+    std::vector<int> planes;
+    std::vector<int> rt_off(t.L), ct_off(t.L), pl_off(t.L), max_cells(t.L, 0), n_in(t.L, 0);
+    int maxA = 1;
+    for (int l = 0; l < t.L; ++l) {
+        const int H = t.H[l], W = t.W[l], A = t.A[l], n0 = t.offs[l];
+        if (W > 128 || A > 255) return cudaSuccess;
+        maxA = std::max(maxA, A);
+        rt_off[l] = (int)(rowtab.size() / 4);
+        ct_off[l] = (int)(coltab.size() / 4);
+        pl_off[l] = (int)(planes.size() / 4);
+        auto at = [&](int r, int c, int a) { return (size_t)(n0 + (r * W + c) * A + a); };
+        for (int a = 0; a < A; ++a)
+            for (int r = 0; r < H; ++r) {
+                const float y0 = cor[at(r, 0, a) * 4 + 0], y1 = cor[at(r, 0, a) * 4 + 2];
+                if (!(y1 - y0 > 0.f)) return cudaSuccess;        // the kernel relies on anchors of positive area
+                rowtab.insert(rowtab.end(), {y0, y1, y1 - y0, 0.f});
+            }
+        for (int a = 0; a < A; ++a)
+            for (int c = 0; c < W; ++c) {
+                const float x0 = cor[at(0, c, a) * 4 + 1], x1 = cor[at(0, c, a) * 4 + 3];
+                if (!(x1 - x0 > 0.f)) return cudaSuccess;
+                coltab.insert(coltab.end(), {x0, x1, x1 - x0, 0.f});
+            }
+        for (int a = 0; a < A; ++a) {
+            const float* rt = rowtab.data() + ((size_t)rt_off[l] + (size_t)a * H) * 4;
+            const float* ct = coltab.data() + ((size_t)ct_off[l] + (size_t)a * W) * 4;
+            for (int r = 1; r < H; ++r)
+                if (!(rt[r * 4] >= rt[(r - 1) * 4] && rt[r * 4 + 1] >= rt[(r - 1) * 4 + 1])) return cudaSuccess;
+            for (int c = 1; c < W; ++c)
+                if (!(ct[c * 4] >= ct[(c - 1) * 4] && ct[c * 4 + 1] >= ct[(c - 1) * 4 + 1])) return cudaSuccess;
+            std::vector<char> rany(H, 0), cany(W, 0);
+            for (int r = 0; r < H; ++r)
+                for (int c = 0; c < W; ++c) {
+                    const size_t n = at(r, c, a);
+                    if (bits(cor[n * 4 + 0]) != bits(rt[r * 4]) || bits(cor[n * 4 + 2]) != bits(rt[r * 4 + 1]) ||
+                        bits(cor[n * 4 + 1]) != bits(ct[c * 4]) || bits(cor[n * 4 + 3]) != bits(ct[c * 4 + 1]))
+                        return cudaSuccess;
+                    if (in[n]) { rany[r] = 1; cany[c] = 1; }
+                }
+            int r0 = H, r1 = -1, c0 = W, c1 = -1, nr = 0, nc = 0;
+            for (int r = 0; r < H; ++r) if (rany[r]) { r0 = std::min(r0, r); r1 = std::max(r1, r); ++nr; }
+            for (int c = 0; c < W; ++c) if (cany[c]) { c0 = std::min(c0, c); c1 = std::max(c1, c); ++nc; }
+            if (nr && (r1 - r0 + 1 != nr || c1 - c0 + 1 != nc)) return cudaSuccess;
+            for (int r = 0; r < H; ++r)
+                for (int c = 0; c < W; ++c)
+                    if ((in[at(r, c, a)] != 0) != (rany[r] && cany[c])) return cudaSuccess;
+            if (!nr) { r0 = 1; r1 = 0; c0 = 1; c1 = 0; }
+            planes.insert(planes.end(), {r0, r1, c0, c1});
+            max_cells[l] = std::max(max_cells[l], nr * nc);
+            n_in[l] += nr * nc;
+        }
+    }
+    // CTA size: the warp count in 6..10 that keeps most warps busy when a warp owns a plane (or one of
+    // floor(warps / A) row sub-bands of it), weighted by the inside anchors of the layers swept that way
+    int dense_cells = 64;
+    if (const char* e = getenv("RONK_ENC_DENSE_CELLS")) dense_cells = atoi(e);       // tuning knob
+    auto is_dense = [&](int l) { return max_cells[l] <= dense_cells && t.offs[l + 1] - t.offs[l] <= 8192; };
+    int best_nw = 8;
+    double best_u = -1.;
+    for (int nw = 6; nw <= 10; ++nw) {
+        double u = 0., wsum = 0.;
+        for (int l = 0; l < t.L; ++l) {
+            if (is_dense(l)) continue;
+            const int A = t.A[l];
+            const double f = A <= nw ? (double)(A * (nw / A)) / nw : (double)A / (((A + nw - 1) / nw) * nw);
+            u += f * n_in[l];
+            wsum += n_in[l];
+        }
+        u = wsum > 0 ? u / wsum : 1.;
+        if (u >= best_u - 1e-9) { best_u = u; best_nw = nw; }
+    }
+    if (const char* e = getenv("RONK_ENC_WARPS")) {                                     // tuning knob
+        const int v = atoi(e);
+        if (v >= 1 && v <= 10) best_nw = v;
+    }
+    h->grid_threads = 32 * best_nw;
+
+    auto compact_lo = [&](int n) { return (int)(std::lower_bound(idx.begin(), idx.end(), n) - idx.begin()); };
+    const int targets[3] = {4096, 2048, 1024};          // anchors per row band: coarse / medium / fine cut
+    for (int tv = 0; tv < 3; ++tv) {
+        std::vector<GridItem> items;
+        std::vector<long long> weight;
+        for (int l = 0; l < t.L;) {
+            GridItem it;
+            memset(&it, 0, sizeof(it));
+            if (is_dense(l)) {
+                // consecutive sparse layers share one dense item
+                int l2 = l, nin = 0;
+                while (l2 < t.L && is_dense(l2) && t.offs[l2 + 1] - t.offs[l] <= 8192 &&
+                       (l2 == l || nin + n_in[l2] <= 1024)) {
+                    nin += n_in[l2];
+                    ++l2;
+                }
+                it.mode = 1;
+                it.n_lo = t.offs[l];
+                it.n_hi = t.offs[l2];
+                it.c_lo = compact_lo(it.n_lo);
+                it.c_hi = compact_lo(it.n_hi);
+                items.push_back(it);
+                weight.push_back(it.c_hi - it.c_lo);
+                l = l2;
+                continue;
+            }
+            const int H = t.H[l], W = t.W[l], A = t.A[l];
+            int rows_max = std::max(1, targets[tv] / (W * A));
+            rows_max = std::min(rows_max, 255);
+            const int nb = (H + rows_max - 1) / rows_max;
+            const int rows = (H + nb - 1) / nb;
+            if ((long long)rows * W * A > 8192) return cudaSuccess;
+            for (int r_lo = 0; r_lo < H; r_lo += rows) {
+                it.mode = 0;
+                it.r_lo = r_lo;
+                it.rows = std::min(rows, H - r_lo);
+                it.n_lo = t.offs[l] + r_lo * W * A;
+                it.n_hi = it.n_lo + it.rows * W * A;
+                it.H = H; it.W = W; it.A = A;
+                it.rt_base = rt_off[l];
+                it.ct_base = ct_off[l];
+                it.pl_base = pl_off[l];
+                it.layer_n0 = t.offs[l];
+                it.nsub = std::max(1, std::min(best_nw / A, it.rows));
+                int ps = it.rows * W;
+                while (ps % 16 != 3) ++ps;               // spreads the planes over the shared-memory banks
+                it.pstride = ps;
+                it.c_lo = compact_lo(it.n_lo);
+                it.c_hi = compact_lo(it.n_hi);
+                items.push_back(it);
+                weight.push_back(it.c_hi - it.c_lo);
+            }
+            ++l;
+        }
+        // heavy items first (the grid is item-major)
+        std::vector<int> order(items.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
+        std::vector<GridItem> sorted;
+        size_t smem = 0;
+        for (int i : order) {
+            const GridItem& g = items[i];
+            sorted.push_back(g);
+            size_t S = g.mode == 0 ? (size_t)g.A * g.pstride : (size_t)(g.n_hi - g.n_lo);
+            S = (S + 1) & ~(size_t)1;
+            smem = std::max(smem, S * 8 + (g.mode == 0 ? (size_t)g.A * (g.rows + g.W) * 16 : 0));
+        }
+        h->n_gitems[tv] = (int)sorted.size();
+        h->gitems_smem[tv] = smem;
+        cudaError_t e = cudaMalloc(&h->d_gitems[tv], sorted.size() * sizeof(GridItem));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_gitems[tv], sorted.data(), sorted.size() * sizeof(GridItem), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaMalloc(&h->d_rowtab, rowtab.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_coltab, coltab.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_planes, planes.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_rowtab, rowtab.data(), rowtab.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_coltab, coltab.data(), coltab.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_planes, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    h->grid_ok = 1;
+    return cudaSuccess;
+}
+
 cudaError_t finish_compaction(ronk_anchors* h) {
     const int N = h->tab.N;
     std::vector<uint8_t> in(N);
@@ -105,6 +278,9 @@ cudaError_t finish_compaction(ronk_anchors* h) {
     if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_inside_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cidx, cidx.data(), (size_t)N * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(h->d_ccor, ccor.data(), ccor.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+
+    e = build_grid(h, cor, in, idx);
     if (e != cudaSuccess) return e;
 
     // ---- post-process tile table (see common.cuh)
@@ -355,6 +531,11 @@ extern "C" void ronk_anchors_destroy(ronk_anchors_t* h) {
     for (int t = 0; t < 3; ++t)
         if (h->d_items[t]) cudaFree(h->d_items[t]);
     if (h->d_tile_tab) cudaFree(h->d_tile_tab);
+    if (h->d_rowtab) cudaFree(h->d_rowtab);
+    if (h->d_coltab) cudaFree(h->d_coltab);
+    if (h->d_planes) cudaFree(h->d_planes);
+    for (int t = 0; t < 3; ++t)
+        if (h->d_gitems[t]) cudaFree(h->d_gitems[t]);
     delete h;
 }
 

@@ -30,122 +30,9 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "encode_common.cuh"
 
 namespace ronk {
-
-constexpr int kEncApt = 2;                              // anchors per lane
-constexpr int kEncSet = 32 * kEncApt;                   // anchors per warp-set
-
-struct EncodeParams {
-    const float4* cor;        // [N]   corners of every anchor (force phase)
-    const float4* ccor;       // [Nin] corners of the inside anchors
-    const int* inside_idx;    // [Nin] flat index of the inside anchors
-    const int* cidx;          // [N]   compact index or -1
-    const float4* enc;        // [N]   (cy, cx, h', w')
-    const uint8_t* inside;    // [N]
-    int N, Nin, tiles, anchors_nice;
-    const int4* items;        // [tiles] work items {first compact anchor, first flat anchor, end flat anchor, GT split}
-    const float4* gt_boxes;
-    const long long* gt_labels;
-    const int* gt_counts;
-    int B, Gmax, gcap;
-    float high, low;
-    float ps0, ps1, ps2, ps3;
-    int ignore_between, gt_max_first;
-    long long* out_labels;
-    float4* out_loc;
-    float* out_scores;
-    int* out_matched;
-    int* out_obj;
-    u64* ws_keys;             // [B*Gmax] per-GT (iou bits << 32 | ~compact anchor), zero between calls
-    unsigned* ws_claimed;     // [B*Gmax] gt_max_first=False bookkeeping, zero between calls
-    unsigned* ws_count;       // [B] tiles finished per image, zero between calls
-};
-
-// nets/ssd_common.py:130-144: (cx, cy, w, h) ordering, two true divisions per term.
-// encode divides y by ps0, x by ps1, h by ps2, w by ps3 (Appendix A.5 note).
-__device__ __forceinline__ float4 encode_loc(float4 gb, float4 e, const EncodeParams& p) {
-    float gcy = (gb.z + gb.x) / 2.f;
-    float gcx = (gb.w + gb.y) / 2.f;
-    float gh = gb.z - gb.x;
-    float gw = gb.w - gb.y;
-    float t_cy = ((gcy - e.x) / e.z) / p.ps0;
-    float t_cx = ((gcx - e.y) / e.w) / p.ps1;
-    float t_h = log_cr(gh / e.z) / p.ps2;
-    float t_w = log_cr(gw / e.w) / p.ps3;
-    return make_float4(t_cx, t_cy, t_w, t_h);
-}
-
-// branch-free IoU in exactly the reference's op order (ssd_common.py:34-47).
-// NICE: every coordinate is 0 or has a magnitude in [2^-15, 2^15] and no GT side exceeds 1 (checked
-// per anchor handle and per image), so the quotient takes the inline division sequence and the
-// clamps are saturating subtracts; otherwise IEEE div.rn and fmaxf.
-template <bool NICE>
-__device__ __forceinline__ float iou_ref(float4 t, float ga, float4 a, float aa) {
-    float h, w;
-    if (NICE) {
-        // max(d, 0) as a saturating subtract (one FMA-pipe instruction instead of FADD + FMNMX):
-        // exact because d <= the GT side <= 1 (checked per image)
-        h = __saturatef(fminf(t.z, a.z) - fmaxf(t.x, a.x));
-        w = __saturatef(fminf(t.w, a.w) - fmaxf(t.y, a.y));
-    } else {
-        h = fmaxf(fminf(t.z, a.z) - fmaxf(t.x, a.x), 0.f);
-        w = fmaxf(fminf(t.w, a.w) - fmaxf(t.y, a.y), 0.f);
-    }
-    float inter = h * w;
-    float uni = (ga + aa) - inter;
-    // where(union == 0, 0, inter / union); union == 0 implies inter == 0
-    return NICE ? div_overlap_nice(inter, uni) : div_overlap(inter, uni);
-}
-
-__device__ __forceinline__ bool nice_coord(float v) {
-    // 0, or 2^-15 <= |v| <= 2^15 (NaN / inf fail)
-    unsigned e = (__float_as_uint(v) >> 23) & 0xffu;
-    return v == 0.f || (e >= 127u - 15u && e <= 127u + 15u);
-}
-
-// Per image, run by the CTA that finished the image last: g2a[g] = decoded per-GT best anchor
-// (all-zero row -> anchor 0); the lowest GT index that claims an anchor wins; score =
-// overlap[g, n].  Also restores the workspace to zero for the next call.
-template <int NT>
-__device__ void force_image(const EncodeParams& p, int b, int G, int* s_n, int* s_cl) {
-    const int tid = threadIdx.x;
-    for (int g = tid; g < p.Gmax; g += NT) {
-        size_t o = (size_t)b * p.Gmax + g;
-        u64 key = __ldcg(p.ws_keys + o);
-        int n = 0;
-        if (key) n = p.inside_idx[0xffffffffu - (unsigned)(key & 0xffffffffull)];
-        s_n[g] = n;
-        s_cl[g] = p.gt_max_first ? 0 : (int)__ldcg(p.ws_claimed + o);
-        if (key) p.ws_keys[o] = 0ull;
-        if (!p.gt_max_first) p.ws_claimed[o] = 0u;
-    }
-    if (tid == 0) p.ws_count[b] = 0u;
-    __syncthreads();
-    for (int g0 = 0; g0 < G; g0 += NT) {
-        const int g = g0 + tid;
-        const bool act = g < G;
-        const int n = act ? s_n[g] : -1;
-        bool first = act && !s_cl[act ? g : 0];   // gt_max_first=False: a GT that already owns an anchor forces nothing
-        const int lim = min(G, g0 + NT);
-        for (int g2 = 0; g2 < lim; ++g2) first = first && !(g2 < g && s_n[g2] == n && !s_cl[g2]);
-        if (!first) continue;
-        const float4 gb = p.gt_boxes[(size_t)b * p.Gmax + g];
-        const float4 a = p.cor[n];
-        const float4 e = p.enc[n];
-        const bool in = p.inside[n] != 0;
-        const long long label = p.gt_labels[(size_t)b * p.Gmax + g];
-        float iou = iou_ref<false>(gb, (gb.w - gb.y) * (gb.z - gb.x), a, (a.w - a.y) * (a.z - a.x));
-        float ov = iou * (in ? 1.f : 0.f);
-        size_t o = (size_t)b * p.N + n;
-        p.out_labels[o] = label;
-        p.out_loc[o] = encode_loc(gb, e, p);
-        p.out_scores[o] = ov;
-        if (p.out_matched) p.out_matched[o] = g;
-        if (p.out_obj) p.out_obj[o] = label > 0 ? 1 : 0;
-    }
-}
 
 // IoU sweep of one warp over GT boxes [g_lo, g_hi).  best/bestg: per-anchor running max and
 // FIRST argmax over GT (strict '>' over ascending g == tf.argmax first occurrence).
@@ -421,7 +308,7 @@ __device__ __forceinline__ void encode_item(const EncodeParams& p, unsigned char
     if (s_last) {
         __threadfence();
         // s_best (8 B per GT slot) is free now: reuse it as two int arrays
-        force_image<kEncThreads>(p, b, G, reinterpret_cast<int*>(s_best), reinterpret_cast<int*>(s_best) + p.gcap);
+        force_image(p, b, G, reinterpret_cast<int*>(s_best), reinterpret_cast<int*>(s_best) + p.gcap, kEncThreads);
     }
 }
 
@@ -456,6 +343,10 @@ __global__ void zero_u32_kernel(unsigned* p, size_t n) {
 
 }  // namespace ronk
 
+namespace ronk {
+int launch_match_encode_grid(const ronk_anchors* h, EncodeParams& p, int B, cudaStream_t st);   // match_encode_grid.cu
+}
+
 using namespace ronk;
 
 #ifdef RONK_ENC_TRACE
@@ -467,7 +358,8 @@ extern "C" int ronk_debug_set_enc_trace(void* buf) {
 
 extern "C" size_t ronk_encode_workspace_bytes(int B, int Gmax) {
     if (B < 1 || Gmax < 1) return 0;
-    return (size_t)B * Gmax * (sizeof(u64) + sizeof(unsigned)) + (size_t)B * sizeof(unsigned);
+    // per-GT keys + claimed flags, per-image item counters (all zero between calls), image order (scratch)
+    return (size_t)B * Gmax * (sizeof(u64) + sizeof(unsigned)) + (size_t)B * sizeof(unsigned) + (size_t)B * sizeof(int);
 }
 
 extern "C" int ronk_encode_workspace_init(void* ws, int B, int Gmax, void* stream) {
@@ -518,8 +410,16 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     p.ws_keys = (u64*)ws;
     p.ws_claimed = (unsigned*)((u64*)ws + (size_t)B * Gmax);
     p.ws_count = p.ws_claimed + (size_t)B * Gmax;
+    p.order = (const int*)(p.ws_count + B);
 
     p.anchors_nice = h->anchors_nice;
+    p.gitems = nullptr;
+    p.rowtab = p.coltab = nullptr;
+    p.planes = nullptr;
+    p.key_flat = 0;
+    // anchors on the regular grids the reference generates take the grid kernel; arbitrary flattened anchors
+    // (ronk_anchors_create_flat) the generic one below
+    if (h->grid_ok && !getenv("RONK_ENC_GENERIC")) return launch_match_encode_grid(h, p, B, (cudaStream_t)stream);
     // Work-item table: the batch decides how finely the heaviest items are cut.  A tiny batch cannot
     // fill 148 SMs x 40 warps with whole-GT-list items, and the kernel then lasts as long as its
     // slowest CTA (a coarse-layer tile against 50 GT boxes): cut those (table 1) or everything
