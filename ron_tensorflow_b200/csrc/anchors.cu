@@ -163,7 +163,11 @@ static cudaError_t build_grid(ronk_anchors* h, const std::vector<float>& cor, co
     h->grid_threads = 32 * best_nw;
 
     auto compact_lo = [&](int n) { return (int)(std::lower_bound(idx.begin(), idx.end(), n) - idx.begin()); };
-    const int targets[3] = {4096, 2048, 1024};          // anchors per row band: coarse / medium / fine cut
+    int targets[3] = {4096, 2048, 1024};                // anchors per row band: coarse / medium / fine cut
+    if (const char* e = getenv("RONK_ENC_TARGET")) {    // tuning knob: scales the three cuts
+        const int v = atoi(e);
+        if (v >= 256 && v <= 8192) { targets[0] = v; targets[1] = v / 2; targets[2] = v / 4; }
+    }
     for (int tv = 0; tv < 3; ++tv) {
         std::vector<GridItem> items;
         std::vector<long long> weight;

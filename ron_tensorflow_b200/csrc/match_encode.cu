@@ -417,9 +417,19 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     p.rowtab = p.coltab = nullptr;
     p.planes = nullptr;
     p.key_flat = 0;
-    // anchors on the regular grids the reference generates take the grid kernel; arbitrary flattened anchors
-    // (ronk_anchors_create_flat) the generic one below
-    if (h->grid_ok && !getenv("RONK_ENC_GENERIC")) return launch_match_encode_grid(h, p, B, (cudaStream_t)stream);
+    // Anchors on the regular grids the reference generates can take the grid kernel (match_encode_grid.cu): fewer
+    // instructions per image (exact rectangles of intersecting cells instead of a culled dense sweep), but a CTA owns
+    // a whole band of a layer and lives 2-3x longer, so it only pays once the batch fills the machine several times
+    // over (measured crossover for RON-320: ~110 images).  Arbitrary flattened anchors (ronk_anchors_create_flat)
+    // and small batches take the generic kernel below.
+    {
+        int use_grid = h->grid_ok && (long long)B * h->tab.N >= 2400000ll;
+        if (const char* e = getenv("RONK_ENC_KERNEL")) {           // tuning knob: "grid" / "generic"
+            if (e[0] == 'g' && e[1] == 'r') use_grid = h->grid_ok;
+            else if (e[0] == 'g' && e[1] == 'e') use_grid = 0;
+        }
+        if (use_grid) return launch_match_encode_grid(h, p, B, (cudaStream_t)stream);
+    }
     // Work-item table: the batch decides how finely the heaviest items are cut.  A tiny batch cannot
     // fill 148 SMs x 40 warps with whole-GT-list items, and the kernel then lasts as long as its
     // slowest CTA (a coarse-layer tile against 50 GT boxes): cut those (table 1) or everything

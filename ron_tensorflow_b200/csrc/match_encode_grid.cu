@@ -496,10 +496,9 @@ namespace ronk {
 #endif
 
 int launch_match_encode_grid(const ronk_anchors* h, EncodeParams& p, int B, cudaStream_t st) {
-    // Item table: the batch decides how finely the layers are cut into row bands.  Few images cannot fill 148 SMs
-    // with whole-layer items; many images prefer the coarsest cut (least per-item overhead).
-    const long long work = (long long)B * h->tab.N;
-    int table = work >= 3000000 ? 0 : (work >= 700000 ? 1 : 2);
+    // Item table: bands of ~4096 anchors measured best at every batch size this kernel is dispatched for (finer cuts
+    // pay the per-CTA fixed cost -- prologue, fence + counter -- more often); the other two tables stay selectable.
+    int table = 0;
     if (const char* e = getenv("RONK_ENC_TABLE")) {             // tuning knob
         const int v = atoi(e);
         if (v >= 0 && v <= 2) table = v;

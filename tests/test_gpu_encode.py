@@ -11,6 +11,14 @@ from _util import need_cuda, eq, close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=['generic', 'grid'])
+def encode_kernel(request, monkeypatch):
+    """Every test of this module runs once per match+encode kernel: the batch size alone would send the small
+    cases to the generic kernel only (csrc/match_encode.cu dispatches on B * N; RONK_ENC_KERNEL overrides it)."""
+    monkeypatch.setenv('RONK_ENC_KERNEL', request.param)
+    return request.param
+
+
 @pytest.fixture(scope='module')
 def ron():
     need_cuda()

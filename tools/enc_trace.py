@@ -19,7 +19,7 @@ _ffi.LIB_PATH = OUT
 from ron_tensorflow_b200 import core, synth
 from ron_tensorflow_b200.nets import ron_vgg_320
 L = _ffi.lib()
-setter = getattr(ctypes.CDLL(OUT), 'ronk_debug_set_enc_trace' if os.environ.get('RONK_ENC_GENERIC') else 'ronk_debug_set_enc_trace_grid')
+setter = getattr(ctypes.CDLL(OUT), 'ronk_debug_set_enc_trace' if os.environ.get('RONK_ENC_KERNEL', 'grid').startswith('ge') else 'ronk_debug_set_enc_trace_grid')
 setter.argtypes = [ctypes.c_void_p]
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 aset = ron_vgg_320.RONNet().anchors((320, 320)).anchor_set
@@ -57,7 +57,7 @@ heavy = np.argsort(-dur)[:10]
 print('10 longest CTAs: ' + ' '.join('(start %.1f dur %.1f)' % (st[i], dur[i]) for i in heavy))
 ph = (t[:, [3, 4, 5, 6, 2]] - t[:, [0, 3, 4, 5, 6]]) / 1e3
 names = ['load+stage', 'sweep', 'output', 'fence+counter', 'force/exit']
-if not os.environ.get('RONK_ENC_GENERIC'):
+if not os.environ.get('RONK_ENC_KERNEL', 'grid').startswith('ge'):
     print('sweep of warp 0 vs whole CTA (us): %.2f / %.2f' % (((t[:, 7] - t[:, 3]) / 1e3).mean(), ((t[:, 4] - t[:, 3]) / 1e3).mean()))
 for sel, what in ((slice(None), 'all CTAs'), (late, 'last 64 started'), (order[:1184], 'first wave'), (order[1500:2500], 'middle')):
     print('%-16s ' % what + '  '.join('%s %.2f' % (n, v) for n, v in zip(names, ph[sel].mean(0))) + '   (mean us per phase)')
