@@ -495,6 +495,12 @@ extern "C" int ronk_debug_set_enc_trace_grid(void* buf) {
 namespace ronk {
 #endif
 
+int launch_rank_images(const EncodeParams& p, int B, cudaStream_t st) {
+    rank_images_kernel<<<(B + 255) / 256, 256, 0, st>>>(p.gt_counts, B, p.Gmax, const_cast<int*>(p.order));
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
 int launch_match_encode_grid(const ronk_anchors* h, EncodeParams& p, int B, cudaStream_t st) {
     // Item table: bands of ~4096 anchors measured best at every batch size this kernel is dispatched for (finer cuts
     // pay the per-CTA fixed cost -- prologue, fence + counter -- more often); the other two tables stay selectable.
@@ -510,8 +516,7 @@ int launch_match_encode_grid(const ronk_anchors* h, EncodeParams& p, int B, cuda
     p.planes = (const int4*)h->d_planes;
     p.key_flat = 1;
     RONK_REQUIRE(B <= 65535, RONK_ELIMIT, "ronk_match_encode: more than 65535 images in one call");
-    rank_images_kernel<<<(B + 255) / 256, 256, 0, st>>>(p.gt_counts, B, p.Gmax, const_cast<int*>(p.order));
-    RONK_LAUNCHED();
+    if (int rc = launch_rank_images(p, B, st)) return rc;
     const size_t smem = h->gitems_smem[table] + (size_t)p.gcap * (kGtRec + 8 + 8) + (size_t)kPosCap * 4;
     RONK_REQUIRE(smem <= 200 * 1024, RONK_ELIMIT, "ronk_match_encode: item state does not fit in shared memory");
     if (smem > 48 * 1024)
