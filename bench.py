@@ -32,10 +32,10 @@ ENC_B, ENC_G = 64, (1, 50)
 ENC_STREAMS = int(os.environ.get("RONK_BENCH_ENC_STREAMS", "2"))      # steps are issued round-robin on this many CUDA streams for `value`
 POST_STREAMS = int(os.environ.get("RONK_BENCH_POST_STREAMS", "3"))
 WORKLOAD = ('BASELINE configs[1]: RON-320 joint match+encode over all 4 layers (21250 anchors), batch 64 per GPU, '
-            '1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels')
+            '1-50 GT/image, thresholds 0.56/0.3, objectness-prior labels (labels i64, localisations, scores, objectness i32 written)')
 POST_B, POST_K, POST_M, POST_THR = 256, 400, 200, 0.45
 N_ANCHORS, N_CLASSES = 21250, 21
-ENC_BYTES_PER_IMAGE = N_ANCHORS * 28          # labels i64 + loc 4xf32 + score f32; + 24 B per GT
+ENC_BYTES_PER_IMAGE = N_ANCHORS * 32          # labels i64 + loc 4xf32 + score f32 + objectness label i32; + 24 B per GT
 POST_BYTES_PER_IMAGE = N_ANCHORS * (4 * N_CLASSES + 16 + 4) + (N_CLASSES - 1) * POST_M * 20
 
 
@@ -257,20 +257,30 @@ def pipelined_steps(torch, step, nstreams, steps, warmup, graph=False):
             g = None
             torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pipelined_steps.stats = None
     if g is not None:
+        # The graph holds exactly `steps` steps.  It is replayed R times back to back (R >= 50 and long enough for a
+        # timed region of >= 60 ms), an event between replays: the reported time is the MEDIAN replay, the spread
+        # (p10 / p90 / min / max) rides in the JSON line.
         a.record(main)
         g.replay()
         b.record(main)
         torch.cuda.synchronize()
+        first = max(a.elapsed_time(b), 1e-3)
+        R = int(min(4000, max(50, np.ceil(60.0 / first))))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+        evs[0].record(main)
+        for i in range(R):
+            g.replay()
+            evs[i + 1].record(main)
+        torch.cuda.synchronize()
+        ts = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(R)])
         pipelined_steps.launches = launches
-        if os.environ.get('RONK_BENCH_VERBOSE'):           # spread of further replays, diagnostics only
-            extra = []
-            for _ in range(5):
-                c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                c.record(main); g.replay(); d.record(main); torch.cuda.synchronize()
-                extra.append(c.elapsed_time(d))
-            sys.stderr.write('bench: timed replay %.4f ms, further replays %s\n' % (a.elapsed_time(b), ['%.4f' % v for v in extra]))
-        return a.elapsed_time(b)
+        pipelined_steps.stats = {'replays': R, 'timed_region_ms': float(evs[0].elapsed_time(evs[R])),
+                                 'ms_per_step_median': float(np.median(ts)) / steps, 'ms_per_step_p10': float(np.percentile(ts, 10)) / steps,
+                                 'ms_per_step_p90': float(np.percentile(ts, 90)) / steps, 'ms_per_step_min': float(ts.min()) / steps,
+                                 'ms_per_step_max': float(ts.max()) / steps}
+        return float(np.median(ts))
     l0 = core.launch_count()
     a.record(main)
     issue(0, steps, main)
@@ -360,14 +370,16 @@ def run_ours(args):
     d_boxes = torch.from_numpy(boxes).to(dev)
     d_labels = torch.from_numpy(labels).to(dev)
     d_counts = torch.from_numpy(counts).to(dev)
-    def new_out(B):
-        return dict(labels=torch.empty((B, N), dtype=torch.int64, device=dev),
-                    loc=torch.empty((B, N, 4), dtype=torch.float32, device=dev),
-                    scores=torch.empty((B, N), dtype=torch.float32, device=dev))
+    def new_out(B, n=None):
+        n = n or N
+        return dict(labels=torch.empty((B, n), dtype=torch.int64, device=dev),
+                    loc=torch.empty((B, n, 4), dtype=torch.float32, device=dev),
+                    scores=torch.empty((B, n), dtype=torch.float32, device=dev),
+                    objness=torch.empty((B, n), dtype=torch.int32, device=dev))
     out = new_out(ENC_B)
 
     def enc_step():
-        core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, out=out)
+        core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, want_objness=True, out=out)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -380,12 +392,13 @@ def run_ours(args):
     outs_pipe = [new_out(ENC_B) for _ in range(8)]
 
     def enc_pipe_step(k):
-        core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, out=outs_pipe[k % 8])
+        core.match_encode(aset, d_boxes, d_labels, d_counts, 0.56, 0.3, net.params.prior_scaling, want_objness=True, out=outs_pipe[k % 8])
 
     barrier()
     ms_pipe = pipelined_steps(torch, enc_pipe_step, ENC_STREAMS, args.steps, args.warmup, graph=True)
     enc_launches = pipelined_steps.launches
     enc_graphed = pipelined_steps.graphed
+    enc_stats = pipelined_steps.stats
     barrier()
     del outs_pipe
     t_enc = max_over_ranks(ms_pipe / 1e3)
@@ -402,7 +415,7 @@ def run_ours(args):
     it2 = [0]
 
     def enc256_step():
-        core.match_encode(aset, d2[0], d2[1], d2[2], 0.56, 0.3, net.params.prior_scaling, out=outs2[it2[0] % 4])
+        core.match_encode(aset, d2[0], d2[1], d2[2], 0.56, 0.3, net.params.prior_scaling, want_objness=True, out=outs2[it2[0] % 4])
         it2[0] += 1
 
     barrier()
@@ -410,13 +423,15 @@ def run_ours(args):
     barrier()
     # whole-job throughput like the headline: the K steps on 2 streams, replayed from one CUDA graph
     ms256_pipe = pipelined_steps(torch, lambda k: core.match_encode(aset, d2[0], d2[1], d2[2], 0.56, 0.3, net.params.prior_scaling,
-                                                                    out=outs2[k % 4]), ENC_STREAMS, args.steps, args.warmup, graph=True)
+                                                                    want_objness=True, out=outs2[k % 4]), ENC_STREAMS, args.steps,
+                                 args.warmup, graph=True)
     barrier()
     t256 = max_over_ranks(ms256_pipe / 1e3)
     enc256_bytes = B2 * ENC_BYTES_PER_IMAGE + int(counts2.sum()) * 24
     enc256 = {'metric': 'images/sec (match+encode)', 'value': B2 * args.steps * world / t256, 'unit': 'images/s',
               'ms_per_step': ms256_pipe / args.steps, 'single_stream_ms_per_step': float(np.mean(ms256)),
-              'config': {'workload': 'same path, batch 256 per GPU', 'l2': 'outputs (152 MB/step, 4 rotating sets) exceed L2',
+              'single_stream_ms_per_step_median': float(np.median(ms256)), 'replay_spread': pipelined_steps.stats,
+              'config': {'workload': 'same path, batch 256 per GPU', 'l2': 'outputs (174 MB/step, 4 rotating sets) exceed L2',
                          'pipelining': 'value / ms_per_step as for the headline (2 streams, %s); roofline: single stream'
                                        % ('CUDA graph replay' if pipelined_steps.graphed else 'eager launches')},
               'roofline': {'bound': 'hbm', 'achieved': enc256_bytes / (np.mean(ms256) * 1e-3) / 1e9, 'peak': hbm,
@@ -459,6 +474,7 @@ def run_ours(args):
             raise RuntimeError('bench: host-buffer encode result differs from the device result (%s)' % name)
     enc_h2d = boxes.nbytes + labels.nbytes + counts.nbytes
     enc_d2h = host_enc.d2h_bytes_per_step
+    host_threads = host_enc.threads
     enc_d2h_dense = sum(v.numel() * v.element_size() for v in h_last.values())
     del host_enc
 
@@ -495,6 +511,7 @@ def run_ours(args):
         ms_ppipe = pipelined_steps(torch, post_pipe_step, POST_STREAMS, args.steps, args.warmup, graph=True)
         post_graphed = pipelined_steps.graphed
         post_launches = pipelined_steps.launches
+        post_stats = pipelined_steps.stats
         barrier()
         t_post = max_over_ranks(ms_ppipe / 1e3)
         post_value = POST_B * args.steps * world / t_post
@@ -540,7 +557,8 @@ def run_ours(args):
         post = {
             'metric': 'images/sec (decode+select+NMS)', 'value': post_value, 'unit': 'images/s',
             'ms_per_step': ms_ppipe / args.steps,
-            'single_stream_ms_per_step': float(np.mean(ms_p)),
+            'single_stream_ms_per_step': float(np.mean(ms_p)), 'single_stream_ms_per_step_median': float(np.median(ms_p)),
+            'replay_spread': post_stats,
             'config': {'workload': 'BASELINE configs[2]: RON-320 eval post-process, batch %d per GPU, objectness 0.03, '
                                    'select 0.01, clip, min-size 0.03, top-k %d, NMS min-area %.2f keep %d, + VOC TP/FP kernel'
                                    % (POST_B, POST_K, POST_THR, POST_M), 'l2': 'inputs (586 MB) exceed L2',
@@ -620,6 +638,177 @@ def run_ours(args):
                                  'unit': 'GB/s', 'frac': lm_bytes / (float(np.mean(ms_l)) * 1e-3) / 1e9 / hbm, 'traffic': None},
                     'config': {'workload': 'ron_losses masks (ron_vgg_320.py:686-740) + localisation loss (:760-764) on the '
                                            'targets of one batch of %d RON-320 images; uniforms are inputs; L2 flushed' % ENC_B}}
+    # ---------------------------------------------------------------- BASELINE configs[3]: SSD-512 anchor set, batch 128
+    def graph_loop(fn, nsteps):
+        """One step captured into a CUDA graph and replayed nsteps times (events around the whole loop): ms total."""
+        fn(); fn(); torch.cuda.synchronize()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        l0 = core.launch_count()
+        with torch.cuda.graph(g, stream=cap):
+            fn()
+        per_step = core.launch_count() - l0
+        torch.cuda.current_stream().wait_stream(cap)
+        g.replay(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(nsteps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b), per_step * nsteps
+
+    def roof(bytes_per_step, ms_step, note=None):
+        ach = bytes_per_step / (ms_step * 1e-3) / 1e9
+        r = {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None}
+        if note:
+            r['note'] = note
+        return r
+
+    ssd512 = None
+    if not args.no_postprocess:
+        from ron_tensorflow_b200.nets import ssd_vgg_512
+        net5 = ssd_vgg_512.SSDNet()
+        a5 = net5.anchors(net5.params.img_shape).anchor_set
+        N5, B5 = a5.N, 128
+        b5, l5, c5 = rank_gt_batch(synth, 4, B5, 1, 50, rank)
+        dg5 = [torch.from_numpy(x).to(dev) for x in (b5, l5, c5)]
+        outs5 = [new_out(B5, N5) for _ in range(4)]          # 100 MB per set
+        it5 = [0]
+
+        def enc5_step():
+            core.match_encode(a5, dg5[0], dg5[1], dg5[2], 0.5, 0.5, net5.params.prior_scaling, want_objness=True, out=outs5[it5[0] % 4])
+            it5[0] += 1
+
+        barrier()
+        ms5 = timed_steps(torch, enc5_step, args.steps, args.warmup)
+        barrier()
+        ms5_pipe = pipelined_steps(torch, lambda k: core.match_encode(a5, dg5[0], dg5[1], dg5[2], 0.5, 0.5, net5.params.prior_scaling,
+                                                                      want_objness=True, out=outs5[k % 4]), ENC_STREAMS, args.steps,
+                                   args.warmup, graph=True)
+        enc5_stats = pipelined_steps.stats
+        barrier()
+        t5 = max_over_ranks(ms5_pipe / 1e3)
+        del outs5
+        enc5_bytes = B5 * N5 * 32 + int(c5.sum()) * 24
+        loc5, pred5, _ = synth.make_predictions(4000 + rank, B5, N5, N_CLASSES, hot=300)
+        ls5 = a5.layer_sizes
+        dl5 = [torch.from_numpy(t).to(dev) for t in synth.split_layers(loc5, ls5)]
+        dp5 = [torch.from_numpy(t).to(dev) for t in synth.split_layers(pred5, ls5)]
+
+        def post5_step():
+            return net5.detect(dp5, dl5, 0.01, POST_THR, POST_K, POST_M)
+
+        barrier()
+        ms5p = timed_steps(torch, post5_step, args.steps, args.warmup)      # inputs (314 MB) exceed L2
+        post5_launches = timed_steps.launches
+        barrier()
+        ms5p_pipe = pipelined_steps(torch, lambda k: post5_step(), POST_STREAMS, args.steps, args.warmup, graph=True)
+        post5_stats = pipelined_steps.stats
+        barrier()
+        t5p = max_over_ranks(ms5p_pipe / 1e3)
+        post5_bytes = B5 * (N5 * (4 * N_CLASSES + 16) + (N_CLASSES - 1) * POST_M * 20)
+        ssd512 = {
+            'config': {'workload': 'BASELINE configs[3]: SSD-512 anchor set (%d anchors, 7 layers, no border mask) through the same '
+                                   'kernels, batch %d per GPU' % (N5, B5), 'l2': 'outputs / inputs of one step exceed L2'},
+            'encode': {'metric': 'images/sec (match+encode)', 'value': B5 * args.steps * world / t5, 'unit': 'images/s',
+                       'ms_per_step': ms5_pipe / args.steps, 'single_stream_ms_per_step': float(np.mean(ms5)),
+                       'replay_spread': enc5_stats, 'roofline': roof(enc5_bytes, float(np.mean(ms5))),
+                       'workload': '1-50 GT/image, thresholds 0.5/0.5, labels + localisations + scores + objectness labels'},
+            'postprocess': {'metric': 'images/sec (decode+select+NMS)', 'value': B5 * args.steps * world / t5p, 'unit': 'images/s',
+                            'ms_per_step': ms5p_pipe / args.steps, 'single_stream_ms_per_step': float(np.mean(ms5p)),
+                            'replay_spread': post5_stats, 'gpu_launches': post5_launches,
+                            'roofline': roof(post5_bytes, float(np.mean(ms5p))),
+                            'workload': 'SSD order (ssd_vgg_512.py:182-201): decode, select 0.01, top-k %d, NMS min-area %.2f keep %d; '
+                                        'no objectness, no clip / min-size' % (POST_K, POST_THR, POST_M)},
+        }
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import ron_oracle as O
+            o_anch = O.anchors_all_layers(O.SSD512)
+            o_enc, o_cor, o_in = O.encode_anchor_tables(o_anch, O.SSD512.img_shape, None)
+            n_c = 24
+            t0 = time.perf_counter()
+            for b in range(n_c):
+                O.encode_image(l5[b, :c5[b]], b5[b, :c5[b]], o_enc, o_cor, o_in, 0.5, 0.5)
+            ssd512['encode']['cpu_baseline'] = {'value': n_c / (time.perf_counter() - t0), 'unit': 'images/s', 'cores': 1, 'kind': 'port',
+                                                'sample': 'first %d images of the batch, oracle, 1 thread' % n_c}
+            o_dec = O.flat_decode_anchors(o_anch)
+            n_c = 6
+            t0 = time.perf_counter()
+            for b in range(n_c):
+                O.detected_bboxes_image(pred5[b], loc5[b], o_dec, None, None, 0.01, POST_THR, None, POST_K, POST_M, min_size=None)
+            ssd512['postprocess']['cpu_baseline'] = {'value': n_c / (time.perf_counter() - t0), 'unit': 'images/s', 'cores': 1,
+                                                     'kind': 'port', 'sample': 'first %d images of the batch, oracle, 1 thread' % n_c}
+        del dl5, dp5, loc5, pred5
+
+    # ---------------------------------------------------------------- BASELINE configs[4]: crowded scenes, 10k images sharded
+    crowded = None
+    if not args.no_postprocess:
+        CC, BC, TOTAL = 81, 16, 10000
+        per_gpu = (TOTAL + world - 1) // world
+        nsteps = (per_gpu + BC - 1) // BC
+        if args.steps < 20:                                   # short smoke runs: a bounded slice of the shard
+            nsteps = min(nsteps, 4 * args.steps)
+        locc, predc, objc = synth.make_predictions(5005 + rank, BC, N, CC, hot=2000, dense=True)
+        objc = np.maximum(objc, np.float32(0.05))
+        ls = aset.layer_sizes
+        dlc = [torch.from_numpy(t).to(dev) for t in synth.split_layers(locc, ls)]
+        dpc = [torch.from_numpy(t).to(dev) for t in synth.split_layers(predc, ls)]
+        doc = [torch.from_numpy(t).to(dev) for t in synth.split_layers(objc, ls)]
+        crowded = {'config': {'workload': 'BASELINE configs[4]: crowded scenes, %d images sharded over %d GPU(s) (%d batches of %d per GPU; '
+                                          'one synthetic batch per rank, device resident, reused for every step), %d classes, dense '
+                                          'scores (~10k candidates per class before top-k), 120-200 GT boxes per image'
+                                          % (TOTAL, world, nsteps, BC, CC), 'l2': 'inputs of one step (117 MB) + key lists (218 MB) exceed L2'}}
+        post_bytes_c = BC * (N * (4 * CC + 16 + 4) + (CC - 1) * POST_M * 20)
+        for Kc in (400, 10000):
+            def postc_step():
+                return net.detect(dpc, dlc, doc, 0.03, 0.004, POST_THR, [0., 0., 1., 1.], Kc, POST_M)
+            barrier()
+            ms_c, launches_c = graph_loop(postc_step, nsteps)
+            barrier()
+            t_c = max_over_ranks(ms_c / 1e3)
+            sc, _, _ = core.decode_select_topk(aset, dlc, dpc, doc, 0.03, 0.004, [0., 0., 1., 1.], 0.03, Kc)
+            crowded['postprocess_k%d' % Kc] = {
+                'metric': 'images/sec (decode+select+NMS)', 'value': nsteps * BC * world / t_c, 'unit': 'images/s',
+                'ms_per_step': ms_c / nsteps, 'steps': nsteps, 'gpu_launches': launches_c,
+                'candidates_per_class_after_topk': float((sc[0] > 0).sum(1).float().mean().item()),
+                'roofline': roof(post_bytes_c, ms_c / nsteps, 'steps back to back on one stream (one-step CUDA graph replayed)')}
+            del sc
+        bgc, lgc, cgc = rank_gt_batch(synth, 5, BC, 120, 200, rank)
+        dgc = [torch.from_numpy(x).to(dev) for x in (bgc, lgc, cgc)]
+        outc = new_out(BC)
+
+        def encc_step():
+            core.match_encode(aset, dgc[0], dgc[1], dgc[2], 0.5, 0.3, net.params.prior_scaling, want_objness=True, out=outc)
+
+        barrier()
+        ms_ec, launches_ec = graph_loop(encc_step, nsteps)
+        barrier()
+        t_ec = max_over_ranks(ms_ec / 1e3)
+        crowded['encode'] = {'metric': 'images/sec (match+encode)', 'value': nsteps * BC * world / t_ec, 'unit': 'images/s',
+                             'ms_per_step': ms_ec / nsteps, 'steps': nsteps, 'gpu_launches': launches_ec,
+                             'roofline': roof(BC * N * 32 + int(cgc.sum()) * 24, ms_ec / nsteps,
+                                              'outputs (11 MB per step) stay in L2: one output set, steps back to back')}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import ron_oracle as O
+            o_dec = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+            t0 = time.perf_counter()
+            O.detected_bboxes_image(predc[0], locc[0], o_dec, objc[0], 0.03, 0.004, POST_THR, [0., 0., 1., 1.], 400, POST_M)
+            crowded['postprocess_k400']['cpu_baseline'] = {'value': 1. / (time.perf_counter() - t0), 'unit': 'images/s', 'cores': 1,
+                                                           'kind': 'port', 'sample': '1 image, oracle, 1 thread'}
+            t0 = time.perf_counter()
+            O.detected_bboxes_image(predc[0], locc[0], o_dec, objc[0], 0.03, 0.004, POST_THR, [0., 0., 1., 1.], 10000, POST_M)
+            crowded['postprocess_k10000']['cpu_baseline'] = {'value': 1. / (time.perf_counter() - t0), 'unit': 'images/s', 'cores': 1,
+                                                             'kind': 'port', 'sample': '1 image, oracle, 1 thread'}
+            o_enc, o_cor, o_in = O.encode_anchor_tables(O.anchors_all_layers(O.RON320), (320, 320), [32, 16, 8, 4])
+            t0 = time.perf_counter()
+            for b in range(4):
+                O.encode_image(lgc[b, :cgc[b]], bgc[b, :cgc[b]], o_enc, o_cor, o_in, 0.5, 0.3)
+            crowded['encode']['cpu_baseline'] = {'value': 4. / (time.perf_counter() - t0), 'unit': 'images/s', 'cores': 1, 'kind': 'port',
+                                                 'sample': '4 images, oracle, 1 thread'}
+        del dlc, dpc, doc
+
     clocks = sampler.stop()
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
@@ -637,15 +826,17 @@ def run_ours(args):
     if rank == 0:
         line = {
             'metric': 'images/sec (match+encode)', 'value': enc_value, 'unit': 'images/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_pipe / args.steps, 'higher_is_better': True,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_pipe / args.steps, 'replay_spread': enc_stats,
+            'single_stream_ms_per_step': float(np.mean(ms)), 'single_stream_ms_per_step_median': float(np.median(ms)),
+            'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD,
                        'pipelining': 'value / ms_per_step: %d steps back to back, round-robin on %d CUDA streams, 8 rotating output '
-                                     'sets (305 MB > L2)%s; roofline: the same step alone on one stream, CUDA events around each '
+                                     'sets (348 MB > L2)%s (median of the replays, see replay_spread); roofline: the same step alone on one stream, CUDA events around each '
                                      'launch, L2 flushed between steps (512 MB write): %.4f ms per step'
                                      % (args.steps, ENC_STREAMS, ', replayed from one CUDA graph' if enc_graphed else ', eager launches',
                                         float(np.mean(ms))),
-                       'l2': 'outputs rotate over 305 MB (> 126 MB L2) in the pipelined run; flushed in the single-stream run'},
+                       'l2': 'outputs rotate over 348 MB (> 126 MB L2) in the pipelined run; flushed in the single-stream run'},
             'roofline': {'bound': 'hbm', 'achieved': enc_achieved, 'peak': hbm, 'unit': 'GB/s',
                          'frac': enc_achieved / hbm, 'traffic': traffic('match_encode_b64'), 'peak_source': peak_src,
                          'note': 'algorithmic %d B/batch, one match_encode_kernel launch per step; the kernel is FP32-issue '
@@ -655,11 +846,13 @@ def run_ours(args):
             'e2e': {'value': enc_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': int(enc_h2d),
                     'd2h_bytes_per_step': int(enc_d2h), 'dense_result_bytes_per_step': int(enc_d2h_dense),
                     'note': 'core.HostEncoder, 2 slots: the localisations return as a packet of their non-zero rows (fixed '
-                            'capacity) applied to a pinned host array kept zero elsewhere, labels and scores dense; host '
-                            'clock between device synchronisations; the host result is checked against the device tensors'},
+                            'capacity) applied to a pinned host array kept zero elsewhere; labels (int64) and scores dense: host-side '
+                            'expansion of smaller wire formats measured slower than the DMA write (DESIGN.md 5; %d host threads available); host clock between device synchronisations; the host result (dense labels int64, '
+                            'localisations, scores) is checked against the device tensors' % host_threads},
             'gpu_launches': int(enc_launches),
             'clocks': clocks,
-            'stages': {'encode_b256': enc256, 'postprocess': post, 'ron_eval_single_image': roneval, 'loss_masks_b64': lossmask},
+            'stages': {'encode_b256': enc256, 'postprocess': post, 'ssd512_b128': ssd512, 'crowded': crowded,
+                       'ron_eval_single_image': roneval, 'loss_masks_b64': lossmask},
         }
         print_line(json.dumps(line))
     if world > 1:

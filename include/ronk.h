@@ -321,6 +321,18 @@ int ronk_voc_match(const double* det_boxes, const int32_t* det_offsets, const do
  * ones; the array must be zero elsewhere.  Returns 1, touching nothing, when the packet overflowed (n > cap): copy
  * the dense tensor instead and zero the array before the next sparse step.  Labels and scores are copied dense. */
 size_t ronk_sparse_rows_packet_bytes(int cap);
+/* Labels of the same path: 0 (background) for ~95 % of the anchors.  ronk_sparse_labels_pack packs the non-zero
+ * entries of labels int64 [T] as (index, int32 value) pairs into a packet of ronk_sparse_labels_packet_bytes(cap)
+ * bytes.  ronk_host_targets_apply (plain host code, `threads` host threads from a persistent pool) applies a
+ * localisation packet and a label packet to their host arrays in one go: it zeroes what the PREVIOUS packets wrote
+ * (NULL: nothing), then writes the new entries.  It returns a bit mask and leaves the array in question untouched:
+ * 1 = the localisation packet overflowed, 2 = the label packet overflowed or held a label outside int32.  Scores are
+ * copied dense (a DMA write of 4 B per anchor is cheaper than any host-side scatter). */
+size_t ronk_sparse_labels_packet_bytes(int cap);
+int ronk_sparse_labels_pack(const int64_t* labels, long long T, int cap, void* packet_dev, void* stream);
+int ronk_host_targets_apply(const void* loc_packet_host, const void* prev_loc_packet_host, int loc_cap, float* rows_host,
+                            const void* lab_packet_host, const void* prev_lab_packet_host, int lab_cap,
+                            int64_t* labels_host, int threads);
 int ronk_sparse_rows_pack(const float* rows, long long T, int cap, void* packet_dev, void* stream);
 int ronk_host_rows_apply(const void* packet_host, const void* prev_packet_host, int cap, float* rows_host);
 

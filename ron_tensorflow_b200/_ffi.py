@@ -79,6 +79,9 @@ SIGNATURES = {
     'ronk_sparse_rows_packet_bytes': (c_size_t, [c_int]),
     'ronk_sparse_rows_pack': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     'ronk_host_rows_apply': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    'ronk_sparse_labels_packet_bytes': (c_size_t, [c_int]),
+    'ronk_sparse_labels_pack': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    'ronk_host_targets_apply': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
     'ronk_loss_workspace_bytes': (c_size_t, []),
     'ronk_loss_workspace_init': (c_int, [c_void_p, c_void_p]),
     'ronk_loss_masks': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_void_p, c_void_p,

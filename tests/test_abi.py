@@ -50,7 +50,7 @@ def test_argument_errors_without_gpu(ffi):
     assert rc == ffi.RONK_EINVAL and b'kind' in lib.ronk_last_error()
     with pytest.raises(ValueError):
         ffi.check(rc)
-    assert lib.ronk_encode_workspace_bytes(64, 50) == 64 * 50 * 12 + 64 * 4     # 12 B per GT slot + a tile counter per image
+    assert lib.ronk_encode_workspace_bytes(64, 50) == 64 * 50 * 12 + 64 * 8     # 12 B per GT slot + per image a counter and an order slot
     assert lib.ronk_nms_workspace_bytes(10, 400) == 10 * 400 * 4
     rc = lib.ronk_nms_batch(None, None, 1, 1, 0.5, 1, 0, 1, None, None, None, None, None)
     assert rc == ffi.RONK_EINVAL
