@@ -482,9 +482,13 @@ def run_ours(args):
     post = None
     if not args.no_postprocess:
         ls = aset.layer_sizes
-        loc, pred, obj = synth.make_predictions(3000 + rank, POST_B, N, N_CLASSES, hot=300)
-        gboxes, glabels, gcounts = synth.make_gt_batch(3, POST_B, 1, 12, g_max=12, first_image=rank * POST_B)
+        # the same synthetic batch on every rank, rolled by 17 * rank images: equal work per GPU (weak scaling), and
+        # rank 0 can reproduce every rank's inputs for the NCCL check of the evaluation loop below
+        loc, pred, obj = synth.make_predictions(3000, POST_B, N, N_CLASSES, hot=300)
+        gboxes, glabels, gcounts = synth.make_gt_batch(3, POST_B, 1, 12, g_max=12)
         gdiff = np.zeros_like(glabels)
+        if rank:
+            loc, pred, obj, gboxes, glabels, gdiff = (np.roll(a, 17 * rank, axis=0) for a in (loc, pred, obj, gboxes, glabels, gdiff))
         h_loc = [torch.from_numpy(t).pin_memory() for t in synth.split_layers(loc, ls)]
         h_pred = [torch.from_numpy(t).pin_memory() for t in synth.split_layers(pred, ls)]
         h_obj = [torch.from_numpy(t).pin_memory() for t in synth.split_layers(obj, ls)]
@@ -539,21 +543,111 @@ def run_ours(args):
         h_s, h_b = h_ss[0], h_bs[0]
         del d_sets
 
-        # VOC TP/FP records: accumulated on every rank, gathered ONCE with NCCL, AP on rank 0
+        # VOC TP/FP records of ONE batch per rank: appended on the device, gathered ONCE with NCCL, AP on rank 0
+        # (the same measurement as round 1's tpfp_gather: 1 batch per rank)
         n_gt, tp, fp = res['tpfp']
         cls = list(range(1, N_CLASSES))
-        vals, state = tfe.streaming_tp_fp_arrays({c: n_gt[:, c - 1] for c in cls}, {c: tp[:, c - 1] for c in cls},
-                                                 {c: fp[:, c - 1] for c in cls}, {c: res['s'][:, c - 1] for c in cls})
+        one = tfe.TpFpDeviceState(N_CLASSES, capacity=POST_B * (N_CLASSES - 1) * POST_M)
+        one.update(n_gt, tp, fp, res['s'])
         barrier()
         g0 = time.perf_counter()
-        merged = tfe.gather_tp_fp(state, N_CLASSES)
+        merged = tfe.gather_tp_fp(one, N_CLASSES)
         torch.cuda.synchronize()
         gather_ms = (time.perf_counter() - g0) * 1e3
         aps = []
         for c in cls:
-            v = merged[c].value()
-            p_, r_ = tfe.precision_recall(*v)
+            p_, r_ = tfe.precision_recall(*merged[c].value())
             aps.append(tfe.average_precision_voc07(p_, r_))
+        del one
+
+        # ---- the evaluation loop as the reference runs it (eval_ron_network.py:223-324) at VOC07-test size: 4952 images
+        # sharded over the ranks in batches of 256 (whole batches: >= 4952 images in total); per batch decode + gate +
+        # select + NMS + TP/FP matching + record accumulation, all on the device; then ONE gather and AP on the host.
+        # Rank r's batch is rank 0's rolled by 17 r images, so rank 0 can replay every shard and check the NCCL result.
+        VOC_IMAGES = 4952
+        nb = (VOC_IMAGES + world * POST_B - 1) // (world * POST_B)
+        if args.steps < 20:
+            nb = min(nb, max(2, args.steps // 2))
+
+        def shard(r):
+            sh = (lambda t: t) if r == rank else (lambda t: torch.roll(t, shifts=17 * (r - rank), dims=0))
+            return [sh(t) for t in d_pred], [sh(t) for t in d_loc], [sh(t) for t in d_obj], sh(d_gl), sh(d_gb), sh(d_gd)
+
+        def eval_shard(r, state):
+            sp, sl, so, gl_, gb_, gd_ = shard(r)
+            for _ in range(nb):
+                ns, nb_ = net.detect(sp, sl, so, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+                ng_, tp_, fp_ = core.tpfp_match(ns, nb_, gl_, gb_, gd_, 0.5)
+                state.update(ng_, tp_, fp_, ns)
+            return ns, nb_
+
+        cap = nb * POST_B * (N_CLASSES - 1) * POST_M
+        st_warm = tfe.TpFpDeviceState(N_CLASSES, capacity=POST_B * (N_CLASSES - 1) * POST_M * 2)
+        sp, sl, so, gl_, gb_, gd_ = shard(rank)
+        ns, nb_ = net.detect(sp, sl, so, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)
+        st_warm.update(*core.tpfp_match(ns, nb_, gl_, gb_, gd_, 0.5), ns)
+        del st_warm, sp, sl, so
+        state = tfe.TpFpDeviceState(N_CLASSES, capacity=cap)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = core.launch_count()
+        w0 = time.perf_counter()
+        ev0.record()
+        last_s, last_b = eval_shard(rank, state)
+        ev1.record()
+        torch.cuda.synchronize()
+        loop_launches = core.launch_count() - l0
+        t_loop = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)
+        barrier()
+        g0 = time.perf_counter()
+        merged_all = tfe.gather_tp_fp(state, N_CLASSES)
+        torch.cuda.synchronize()
+        eval_gather_ms = (time.perf_counter() - g0) * 1e3
+        g0 = time.perf_counter()
+        all_s, all_b = tfe.gather_detections(last_s, last_b)
+        torch.cuda.synchronize()
+        det_gather_ms = (time.perf_counter() - g0) * 1e3
+        t_total = max_over_ranks(time.perf_counter() - w0)
+        eval_loop = {'metric': 'images/sec (eval loop: post-process + TP/FP + accumulate)', 'value': nb * POST_B * world / t_loop,
+                     'unit': 'images/s', 'images': nb * POST_B * world, 'batches_per_gpu': nb, 'loop_ms': t_loop * 1e3,
+                     'gpu_launches': loop_launches, 'tpfp_gather_ms': eval_gather_ms, 'detections_gather_ms': det_gather_ms,
+                     'detections_gathered_shape': list(all_s.shape), 'wall_ms_loop_plus_gathers': t_total * 1e3,
+                     'records': int(sum(merged_all[c].scores.shape[0] for c in cls)), 'backend': 'nccl' if world > 1 else 'none',
+                     'config': {'workload': 'VOC07-test sized evaluation (>= %d images, %d batches of %d per GPU), BASELINE configs[2] '
+                                            'post-process parameters, records accumulated on the device (tfe.TpFpDeviceState), one '
+                                            'gather of the records (tfe.gather_tp_fp) and one of the last batch of detections '
+                                            '(tfe.gather_detections); gather times are host clock incl. the device->host copy of all '
+                                            'records' % (VOC_IMAGES, nb, POST_B)}}
+        if rank == 0:
+            a0 = time.perf_counter()
+            ap_all = []
+            for c in cls:
+                p_, r_ = tfe.precision_recall(*merged_all[c].value())
+                ap_all.append(tfe.average_precision_voc07(p_, r_))
+            eval_loop['ap_host_ms'] = (time.perf_counter() - a0) * 1e3
+            eval_loop['mAP_voc07_synthetic'] = float(np.mean(ap_all))
+            if world > 1:
+                # the NCCL path against a single-process accumulation of the same shards, rank-major: bit-equal records and AP
+                single = tfe.TpFpDeviceState(N_CLASSES, capacity=cap * world)
+                for r in range(world):
+                    eval_shard(r, single)
+                ref = single.to_host()
+                for c in cls:
+                    same = (ref[c].n_gt == merged_all[c].n_gt and np.array_equal(ref[c].scores, merged_all[c].scores) and
+                            np.array_equal(ref[c].tp, merged_all[c].tp) and np.array_equal(ref[c].fp, merged_all[c].fp))
+                    if not same:
+                        raise RuntimeError('bench: gathered TP/FP records of class %d differ from the single-process accumulation' % c)
+                    p_, r_ = tfe.precision_recall(*ref[c].value())
+                    if tfe.average_precision_voc07(p_, r_) != ap_all[c - 1]:
+                        raise RuntimeError('bench: AP of class %d differs from the single-process accumulation' % c)
+                sp, sl, so, _, _, _ = shard(world - 1)
+                if not torch.equal(all_s[-POST_B:], net.detect(sp, sl, so, 0.03, 0.01, POST_THR, [0., 0., 1., 1.], POST_K, POST_M)[0]):
+                    raise RuntimeError('bench: gathered detections differ from the last rank\'s own result')
+                eval_loop['nccl_check'] = 'records, ground-truth counts and AP07 of all %d classes bit-equal to a single-process accumulation of the %d shards; gathered detections equal' % (len(cls), world)
+                del single
+        del state, merged_all
+        if world > 1:
+            dist.barrier()
         post = {
             'metric': 'images/sec (decode+select+NMS)', 'value': post_value, 'unit': 'images/s',
             'ms_per_step': ms_ppipe / args.steps,
@@ -574,7 +668,10 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(h_s.numel() * 4 + h_b.numel() * 4)},
             'gpu_launches': post_launches,
             'tpfp_gather': {'backend': 'nccl' if world > 1 else 'none', 'ms': gather_ms, 'mAP_voc07_synthetic': float(np.mean(aps)),
-                            'records': int(sum(merged[c].scores.shape[0] for c in cls))},
+                            'records': int(sum(merged[c].scores.shape[0] for c in cls)),
+                            'note': 'one batch per rank, records appended on the device (tfe.TpFpDeviceState), host clock around '
+                                    'tfe.gather_tp_fp incl. the copy of all records to the host'},
+            'eval_loop': eval_loop,
         }
     # ---------------------------------------------------------------- next row: ron_eval.py single image
     roneval = None

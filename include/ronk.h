@@ -181,6 +181,16 @@ int ronk_tpfp_match(const float* det_scores, const float* det_boxes, int B, int 
                     const int64_t* glabels, const float* gboxes, const int64_t* gdifficults, int Gmax,
                     float matching_threshold,
                     int64_t* out_n_gt, uint8_t* out_tp, uint8_t* out_fp, void* stream);
+/* Device-resident form of tfe.streaming_tp_fp_arrays (tf_extended/metrics.py:133-206): the detections of one batch
+ * that pass the reference's filter (score > min_score, 1e-4 in the reference, and tp or fp, :167-175) are appended to
+ * `records` (uint64 [capacity]: score bits << 32 | class index << 8 | fp << 1 | tp) in (class, image, rank) order
+ * behind the earlier batches; n_gt_acc int64 [C-1] accumulates the ground-truth counts.  totals int32 [4] =
+ * {count, count, overflow flag, -} must start zeroed; call_parity = number of earlier calls on these buffers (the two
+ * count slots alternate between "before" and "after").  Nothing is read back: one copy at the end of the evaluation. */
+size_t ronk_tpfp_records_workspace_bytes(int B, int C, int M);
+int ronk_tpfp_records_append(const float* det_scores, const uint8_t* tp, const uint8_t* fp, const int64_t* n_gt,
+                             int B, int C, int M, float min_score, uint64_t* records, int capacity,
+                             int32_t* totals, int call_parity, int64_t* n_gt_acc, void* ws, void* stream);
 
 /* ------------------------------------------------- fine-grained functions
  * One kernel per small reference function, so the whole Python surface is on the GPU:

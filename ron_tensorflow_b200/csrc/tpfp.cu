@@ -108,9 +108,153 @@ tpfp_kernel(const __grid_constant__ TpfpParams p) {
     }
 }
 
+// ---- device-resident TP/FP records (tf_extended/metrics.py:133-206 without the per-batch trip to the host)
+// A record is one detection that survives the reference's filter (:167-175): score > min_score and (tp or fp), packed
+// as (score bits << 32) | (class index << 8) | fp << 1 | tp.  One batch is appended in (class, image, rank) order --
+// per class that is the order of the reference's tf.boolean_mask over the flattened [B, M] tensors -- behind the
+// records of the earlier batches.  totals = {count before, count after, overflow flag, -}: the host flips the roles of
+// the first two slots from call to call, so no call reads a value another block of the same call writes.
+constexpr int kRecTile = 2048;
+
+struct RecParams {
+    const float* scores;        // [B, CM, M]
+    const uint8_t* tp;
+    const uint8_t* fp;
+    const long long* n_gt;      // [B, CM]
+    int B, CM, M;
+    float min_score;
+    long long n;                // CM * B * M
+    int* tile_counts;
+    u64* rec;
+    int cap;
+    int* totals;
+    int slot_in, slot_out;
+    long long* n_gt_acc;        // [CM]
+};
+
+__device__ __forceinline__ bool rec_keep(const RecParams& p, long long e, size_t* src) {
+    const long long per_class = (long long)p.B * p.M;
+    const int c = (int)(e / per_class);
+    const long long r = e - (long long)c * per_class;
+    const int b = (int)(r / p.M), m = (int)(r - (long long)b * p.M);
+    *src = ((size_t)b * p.CM + c) * p.M + m;
+    return p.scores[*src] > p.min_score && (p.tp[*src] | p.fp[*src]);
+}
+
+__global__ void __launch_bounds__(256)
+records_count_kernel(const __grid_constant__ RecParams p) {
+    __shared__ int s_w[8];
+    const long long base = (long long)blockIdx.x * kRecTile;
+    int c = 0;
+    for (int k = threadIdx.x; k < kRecTile; k += 256) {
+        const long long e = base + k;
+        size_t src;
+        c += (e < p.n && rec_keep(p, e, &src)) ? 1 : 0;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        p.tile_counts[blockIdx.x] = t;
+    }
+    if (blockIdx.x == 0)                                   // ground-truth counts of the batch (metrics.py:177,183)
+        for (int cc = threadIdx.x; cc < p.CM; cc += 256) {
+            long long t = 0;
+            for (int b = 0; b < p.B; ++b) t += p.n_gt[(size_t)b * p.CM + cc];
+            p.n_gt_acc[cc] += t;
+        }
+}
+
+__global__ void __launch_bounds__(256)
+records_write_kernel(const __grid_constant__ RecParams p) {
+    __shared__ int s_w[8];
+    __shared__ int s_base;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int c = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 256) c += p.tile_counts[t];
+    c = __reduce_add_sync(full, c);
+    if (lane == 0) s_w[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        const int before = p.totals[p.slot_in];
+        s_base = before + t;
+        if (blockIdx.x == gridDim.x - 1) {
+            const int after = before + t + p.tile_counts[blockIdx.x];
+            p.totals[p.slot_out] = after < p.cap ? after : p.cap;
+            if (after > p.cap) p.totals[2] = 1;
+        }
+    }
+    __syncthreads();
+    int pos = s_base;
+    const long long base = (long long)blockIdx.x * kRecTile;
+    const long long per_class = (long long)p.B * p.M;
+    for (int k0 = 0; k0 < kRecTile; k0 += 256) {
+        const long long e = base + k0 + threadIdx.x;
+        size_t src = 0;
+        const bool keep = e < p.n && rec_keep(p, e, &src);
+        const unsigned m = __ballot_sync(full, keep);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            before += (w < warp) ? s_w[w] : 0;
+            all += s_w[w];
+        }
+        if (keep) {
+            const int o = pos + before + __popc(m & ((1u << lane) - 1u));
+            if (o < p.cap) {
+                const unsigned cls = (unsigned)(e / per_class);
+                p.rec[o] = ((u64)__float_as_uint(p.scores[src]) << 32) | (u64)((cls << 8) | (p.fp[src] ? 2u : 0u) | (p.tp[src] ? 1u : 0u));
+            }
+        }
+        pos += all;
+    }
+}
+
 }  // namespace ronk
 
 using namespace ronk;
+
+extern "C" size_t ronk_tpfp_records_workspace_bytes(int B, int C, int M) {
+    if (B < 1 || C < 2 || M < 1) return 0;
+    const long long n = (long long)(C - 1) * B * M;
+    return (size_t)((n + kRecTile - 1) / kRecTile) * 4;
+}
+
+extern "C" int ronk_tpfp_records_append(const float* det_scores, const uint8_t* tp, const uint8_t* fp, const int64_t* n_gt,
+                                        int B, int C, int M, float min_score, uint64_t* records, int capacity,
+                                        int32_t* totals, int call_parity, int64_t* n_gt_acc, void* ws, void* stream) {
+    RONK_REQUIRE(det_scores && tp && fp && n_gt && records && totals && n_gt_acc && ws, RONK_EINVAL,
+                 "ronk_tpfp_records_append: NULL argument");
+    RONK_REQUIRE(B >= 1 && C >= 2 && C <= (1 << 20) && M >= 1 && capacity >= 1, RONK_EINVAL, "ronk_tpfp_records_append: bad sizes");
+    RecParams p;
+    p.scores = det_scores; p.tp = tp; p.fp = fp; p.n_gt = (const long long*)n_gt;
+    p.B = B; p.CM = C - 1; p.M = M;
+    p.min_score = min_score;
+    p.n = (long long)p.CM * B * M;
+    RONK_REQUIRE(p.n < (1ll << 31), RONK_ELIMIT, "ronk_tpfp_records_append: batch too large");
+    p.tile_counts = (int*)ws;
+    p.rec = (u64*)records;
+    p.cap = capacity;
+    p.totals = totals;
+    p.slot_in = call_parity & 1;
+    p.slot_out = p.slot_in ^ 1;
+    p.n_gt_acc = (long long*)n_gt_acc;
+    const unsigned tiles = (unsigned)((p.n + kRecTile - 1) / kRecTile);
+    cudaStream_t st = (cudaStream_t)stream;
+    records_count_kernel<<<tiles, 256, 0, st>>>(p);
+    RONK_LAUNCHED();
+    records_write_kernel<<<tiles, 256, 0, st>>>(p);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
 
 extern "C" int ronk_tpfp_match(const float* det_scores, const float* det_boxes, int B, int C, int M,
                                const int64_t* glabels, const float* gboxes, const int64_t* gdifficults, int Gmax,

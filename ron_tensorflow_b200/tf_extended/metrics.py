@@ -2,17 +2,18 @@
 ``streaming_tp_fp_arrays`` :133-206, ``precision_recall`` :100-130, ``average_precision_voc07``
 :237-258, ``average_precision_voc12`` :212-234.
 
-The reference accumulates TP/FP records in TF local variables inside one process.  Here the
-records live on the host in float64/bool NumPy arrays (they are tiny), and ``gather_tp_fp``
-is the one collective of the whole path: every rank contributes its per-class
-(score, tp, fp) records and ground-truth counts, NCCL (torch.distributed) all-gathers them
-once at the end of the evaluation, and rank 0 computes AP exactly as the reference does.
+The reference accumulates TP/FP records in TF local variables inside one process.  Here they are
+accumulated per rank -- on the device (``TpFpDeviceState``: nothing is read back per batch) or on the host
+(``streaming_tp_fp_arrays``, the reference's function) -- and ``gather_tp_fp`` / ``gather_detections`` are the
+collectives of the whole path: every rank contributes its (score, tp, fp) records, ground-truth counts and,
+when asked, its detections; NCCL (torch.distributed) all-gathers them once at the end of the evaluation and AP
+is computed exactly as the reference does.
 """
 import numpy as np
 import torch
 
 __all__ = ['streaming_tp_fp_arrays', 'precision_recall', 'average_precision_voc07', 'average_precision_voc12',
-           'TpFpAccumulator', 'gather_tp_fp']
+           'TpFpAccumulator', 'TpFpDeviceState', 'gather_tp_fp', 'gather_detections']
 
 
 def _np(x):
@@ -46,6 +47,81 @@ class TpFpAccumulator(object):
 
     def value(self):
         return self.n_gt, self.scores.shape[0], self.tp, self.fp, self.scores
+
+
+class TpFpDeviceState(object):
+    """The accumulators of ``streaming_tp_fp_arrays`` for all classes, resident on the device: every batch appends its
+    filtered (score, tp, fp) records behind the earlier ones with two small kernels (ronk_tpfp_records_append) and
+    nothing is read back until ``to_host()`` / ``gather_tp_fp`` at the end of the evaluation -- one copy instead of
+    4 x (C - 1) device->host reads per batch.  ``capacity``: records the buffer can hold (an overflow raises at the end)."""
+
+    def __init__(self, num_classes, capacity=1 << 22, device=None):
+        from .. import core
+        core._require_cuda()
+        self.num_classes = int(num_classes)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.capacity = int(capacity)
+        self.records = torch.empty((self.capacity,), dtype=torch.int64, device=self.device)
+        self.totals = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        self.n_gt = torch.zeros((self.num_classes - 1,), dtype=torch.int64, device=self.device)
+        self.calls = 0
+        self._ws = None
+
+    def update(self, num_gbboxes, tp, fp, scores, min_score=1e-4):
+        """num_gbboxes int64 [B,C-1], tp / fp bool or uint8 [B,C-1,M], scores float32 [B,C-1,M] (the outputs of
+        core.tpfp_match and of the NMS), all on this device."""
+        import ctypes
+        from .. import _ffi, core
+        s = core.as_cuda(scores, torch.float32, self.device)
+        t = tp.view(torch.uint8) if tp.dtype == torch.bool else core.as_cuda(tp, torch.uint8, self.device)
+        f = fp.view(torch.uint8) if fp.dtype == torch.bool else core.as_cuda(fp, torch.uint8, self.device)
+        g = core.as_cuda(num_gbboxes, torch.int64, self.device)
+        B, CM, M = (int(v) for v in s.shape)
+        if CM != self.num_classes - 1 or t.shape != s.shape or f.shape != s.shape or tuple(g.shape) != (B, CM):
+            raise ValueError('expected scores / tp / fp [B,%d,M] and num_gbboxes [B,%d]' % (self.num_classes - 1, self.num_classes - 1))
+        L = _ffi.lib()
+        need = int(L.ronk_tpfp_records_workspace_bytes(B, CM + 1, M))
+        if self._ws is None or self._ws.numel() * 4 < need:
+            self._ws = torch.empty(((need + 3) // 4,), dtype=torch.int32, device=self.device)
+        p = lambda x: ctypes.c_void_p(x.data_ptr())
+        with torch.cuda.device(self.device):
+            _ffi.check(L.ronk_tpfp_records_append(p(s.contiguous()), p(t.contiguous()), p(f.contiguous()), p(g.contiguous()), B, CM + 1, M,
+                                                  float(min_score), p(self.records), self.capacity, p(self.totals), self.calls & 1,
+                                                  p(self.n_gt), p(self._ws), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.calls += 1
+        return self
+
+    def count_tensor(self):
+        """int32 device scalar tensor: records so far."""
+        return self.totals[self.calls & 1]
+
+    @staticmethod
+    def _split(records, n_gt, num_classes):
+        """host records (int64 array in arrival order) -> dict class -> TpFpAccumulator (stable per class)."""
+        meta = (records & 0xffffffff).astype(np.uint32)
+        scores = (records >> 32).astype(np.uint32).view(np.float32)
+        cls = (meta >> 8).astype(np.uint16 if num_classes <= 65536 else np.int64)
+        order = np.argsort(cls, kind='stable')                    # radix sort for small integers: O(n)
+        bounds = np.concatenate([[0], np.cumsum(np.bincount(cls, minlength=num_classes - 1))])
+        scores, meta = scores[order], meta[order]
+        out = {}
+        for c in range(1, num_classes):
+            lo, hi = int(bounds[c - 1]), int(bounds[c])
+            acc = TpFpAccumulator()
+            acc.n_gt = int(n_gt[c - 1])
+            acc.scores = scores[lo:hi].copy()
+            acc.tp = (meta[lo:hi] & 1).astype(bool)
+            acc.fp = ((meta[lo:hi] >> 1) & 1).astype(bool)
+            out[c] = acc
+        return out
+
+    def to_host(self):
+        """dict class -> TpFpAccumulator (the state ``streaming_tp_fp_arrays`` would have built), one device->host copy."""
+        tot = self.totals.cpu().numpy()
+        if tot[2]:
+            raise RuntimeError('TpFpDeviceState: more than %d records, raise `capacity`' % self.capacity)
+        n = int(tot[self.calls & 1])
+        return self._split(self.records[:n].cpu().numpy(), self.n_gt.cpu().numpy(), self.num_classes)
 
 
 def streaming_tp_fp_arrays(num_gbboxes, tp, fp, scores, remove_zero_scores=True, metrics_collections=None,
@@ -103,50 +179,107 @@ def average_precision_voc07(precision, recall, name=None):
 
 
 def gather_tp_fp(state, num_classes, group=None):
-    """All-gather the per-class accumulators of every rank (NCCL when the default process group
-    is NCCL, Gloo on CPU test runs): one all_gather of padded (score, tp, fp) records plus one
-    all_reduce(SUM) of the ground-truth counts.  Returns a merged ``state`` on every rank; the
-    concatenation order is rank-major, which is the order a single process would have produced
-    for a contiguous image split."""
+    """All-gather the TP/FP accumulators of every rank (NCCL when the default process group is NCCL, Gloo on CPU test
+    runs) and return the merged per-class ``state`` (dict class -> TpFpAccumulator) on every rank; the concatenation
+    order is rank-major, which is the order a single process would have produced for a contiguous image split.
+    ``state`` is a ``TpFpDeviceState`` (records never left the device: one all_gather of the counts, one
+    all_gather_into_tensor of the packed records, one all_reduce of the ground-truth counts, one copy to the host) or
+    the dict of host accumulators ``streaming_tp_fp_arrays`` returns (same collectives after one upload)."""
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if isinstance(state, TpFpDeviceState):
+        if not multi:
+            return state.to_host()
+        world = dist.get_world_size(group)
+        meta = torch.cat([state.totals[(state.calls & 1):(state.calls & 1) + 1], state.totals[2:3]]).to(torch.int64)
+        all_meta = torch.empty((world, 2), dtype=torch.int64, device=state.device)
+        dist.all_gather_into_tensor(all_meta, meta, group=group)
+        n_gt = state.n_gt.clone()
+        dist.all_reduce(n_gt, op=dist.ReduceOp.SUM, group=group)
+        all_meta = all_meta.cpu().numpy()                       # the one sync before the big gather: its width
+        if all_meta[:, 1].any():
+            raise RuntimeError('TpFpDeviceState: a rank ran out of record capacity (%d)' % state.capacity)
+        width = max(int(all_meta[:, 0].max()), 1)
+        if width > state.capacity:
+            raise RuntimeError('TpFpDeviceState: capacity %d below the widest rank (%d records)' % (state.capacity, width))
+        out = torch.empty((world, width), dtype=torch.int64, device=state.device)
+        dist.all_gather_into_tensor(out, state.records[:width].contiguous(), group=group)
+        host = out.cpu().numpy()
+        rec = np.concatenate([host[r, :int(all_meta[r, 0])] for r in range(world)])
+        # rank-major order per class == stable split of the rank-major concatenation
+        return TpFpDeviceState._split(rec, n_gt.cpu().numpy(), state.num_classes)
+    if not multi:
         return state
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
     dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
     classes = list(range(1, num_classes))
-    counts = torch.tensor([state[c].scores.shape[0] if c in state else 0 for c in classes], dtype=torch.int64, device=dev)
-    n_gt = torch.tensor([state[c].n_gt if c in state else 0 for c in classes], dtype=torch.int64, device=dev)
-    all_counts = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    dist.all_reduce(n_gt, op=dist.ReduceOp.SUM, group=group)
-    width = int(torch.stack(all_counts).sum(1).max().item())
-    rec = torch.zeros((max(width, 1), 2), dtype=torch.float32, device=dev)
-    o = 0
-    for c in classes:
-        if c in state and state[c].scores.shape[0]:
-            n = state[c].scores.shape[0]
-            rec[o:o + n, 0] = torch.from_numpy(state[c].scores).to(dev)
-            rec[o:o + n, 1] = torch.from_numpy(state[c].tp.astype(np.float32) + 2 * state[c].fp.astype(np.float32)).to(dev)
-            o += n
-    all_rec = [torch.empty_like(rec) for _ in range(world)]
-    dist.all_gather(all_rec, rec, group=group)
+    empty = TpFpAccumulator()
+    accs = [state.get(c, empty) for c in classes]
+    counts = torch.tensor([a.scores.shape[0] for a in accs], dtype=torch.int64)
+    # one packed upload: per class block of (score bits << 32 | fp << 1 | tp)
+    packed = np.concatenate([(a.scores.view(np.uint32).astype(np.int64) << 32) | (a.fp.astype(np.int64) << 1) | a.tp.astype(np.int64)
+                             for a in accs]) if int(counts.sum()) else np.zeros((0,), np.int64)
+    head = torch.cat([counts, torch.tensor([a.n_gt for a in accs], dtype=torch.int64)]).to(dev)
+    all_head = torch.empty((world, head.numel()), dtype=torch.int64, device=dev)
+    if backend == 'nccl':
+        dist.all_gather_into_tensor(all_head, head, group=group)
+    else:
+        parts = [torch.empty_like(head) for _ in range(world)]
+        dist.all_gather(parts, head, group=group)
+        all_head = torch.stack(parts)
+    all_head = all_head.cpu().numpy()
+    all_counts = all_head[:, :len(classes)]
+    width = max(int(all_counts.sum(1).max()), 1)
+    rec = torch.zeros((width,), dtype=torch.int64)
+    rec[:packed.shape[0]] = torch.from_numpy(packed)
+    rec = rec.to(dev)
+    if backend == 'nccl':
+        out = torch.empty((world, width), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, rec, group=group)
+    else:
+        parts = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(parts, rec, group=group)
+        out = torch.stack(parts)
+    host = out.cpu().numpy()
     merged = {}
     for i, c in enumerate(classes):
         acc = TpFpAccumulator()
-        acc.n_gt = int(n_gt[i].item())
-        parts_s, parts_t, parts_f = [], [], []
+        acc.n_gt = int(all_head[:, len(classes) + i].sum())
+        blocks = []
         for r in range(world):
-            cnt = all_counts[r].cpu().numpy()
-            off = int(cnt[:i].sum())
-            n = int(cnt[i])
-            blk = all_rec[r][off:off + n].cpu().numpy()
-            parts_s.append(blk[:, 0].astype(np.float32))
-            code = blk[:, 1].astype(np.int64)
-            parts_t.append((code & 1).astype(bool))
-            parts_f.append((code & 2).astype(bool))
-        acc.scores = np.concatenate(parts_s) if parts_s else acc.scores
-        acc.tp = np.concatenate(parts_t) if parts_t else acc.tp
-        acc.fp = np.concatenate(parts_f) if parts_f else acc.fp
+            off = int(all_counts[r, :i].sum())
+            blocks.append(host[r, off:off + int(all_counts[r, i])])
+        blk = np.concatenate(blocks) if blocks else np.zeros((0,), np.int64)
+        acc.scores = (blk >> 32).astype(np.uint32).view(np.float32).copy()
+        acc.tp = (blk & 1).astype(bool)
+        acc.fp = ((blk >> 1) & 1).astype(bool)
         merged[c] = acc
     return merged
+
+
+def gather_detections(scores, bboxes, group=None):
+    """All-gather the final detections of every rank (the reference keeps them for the debug dump and the TP/FP
+    matching, eval_ron_network.py:230-252): scores [B,C-1,M] / bboxes [B,C-1,M,4] (or dicts class -> [B,M] / [B,M,4])
+    -> the same structures for the world_size * B images, rank-major (a contiguous image split).  One
+    all_gather_into_tensor per tensor over NCCL (Gloo on CPU test runs); no-op without a process group."""
+    import torch.distributed as dist
+    if isinstance(scores, dict):
+        keys = sorted(scores.keys())
+        s, b = gather_detections(torch.stack([scores[k] for k in keys], 1), torch.stack([bboxes[k] for k in keys], 1), group)
+        return {k: s[:, i] for i, k in enumerate(keys)}, {k: b[:, i] for i, k in enumerate(keys)}
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return scores, bboxes
+    world = dist.get_world_size(group)
+    outs = []
+    for t in (scores, bboxes):
+        t = t.contiguous()
+        if dist.get_backend(group) == 'nccl':
+            o = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(o, t, group=group)
+        else:
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t, group=group)
+            o = torch.cat(parts, 0)
+        outs.append(o)
+    return outs[0], outs[1]

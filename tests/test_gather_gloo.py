@@ -50,7 +50,13 @@ def _worker(rank, world, port, q):
     for c in merged:
         p, r = tfe.precision_recall(*merged[c].value())
         aps[c] = (tfe.average_precision_voc07(p, r), tfe.average_precision_voc12(p, r))
-    q.put((rank, res, aps))
+    # the other collective of the path: the detections themselves (rank-major = a contiguous image split)
+    rng = np.random.Generator(np.random.PCG64(77 + rank))
+    ds = torch.from_numpy(rng.uniform(size=(3, NUM_CLASSES - 1, 6)).astype(np.float32))
+    db = torch.from_numpy(rng.uniform(size=(3, NUM_CLASSES - 1, 6, 4)).astype(np.float32))
+    gs, gb = tfe.gather_detections(ds, db)
+    dd_s, dd_b = tfe.gather_detections({c: ds[:, c - 1] for c in range(1, NUM_CLASSES)}, {c: db[:, c - 1] for c in range(1, NUM_CLASSES)})
+    q.put((rank, res, aps, gs.numpy(), gb.numpy(), {c: v.numpy() for c, v in dd_s.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -72,7 +78,16 @@ def test_gather_tp_fp_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     single = _accumulate(tfe, [_records(0), _records(1)])
-    for rank, res, aps in got:
+    want_s, want_b = [], []
+    for r in range(2):
+        rng = np.random.Generator(np.random.PCG64(77 + r))
+        want_s.append(rng.uniform(size=(3, NUM_CLASSES - 1, 6)).astype(np.float32))
+        want_b.append(rng.uniform(size=(3, NUM_CLASSES - 1, 6, 4)).astype(np.float32))
+    want_s, want_b = np.concatenate(want_s), np.concatenate(want_b)
+    for rank, res, aps, gs, gb, dd_s in got:
+        assert np.array_equal(gs, want_s) and np.array_equal(gb, want_b)
+        for c in range(1, NUM_CLASSES):
+            assert np.array_equal(dd_s[c], want_s[:, c - 1])
         for c in range(1, NUM_CLASSES):
             n_gt, scores, tp, fp = res[c]
             assert n_gt == single[c].n_gt
@@ -86,3 +101,6 @@ def test_gather_is_identity_without_process_group():
     import ron_tensorflow_b200.tf_extended as tfe
     state = _accumulate(tfe, [_records(0)])
     assert tfe.gather_tp_fp(state, NUM_CLASSES) is state
+    x, y = torch.zeros(2, 3, 4), torch.zeros(2, 3, 4, 4)
+    gx, gy = tfe.gather_detections(x, y)
+    assert gx is x and gy is y

@@ -376,3 +376,43 @@ def test_cuda_graph_replay_matches_direct_calls(ron):
         assert torch.equal(r1[k], r2[k])
     r3 = ge.replay()
     assert torch.equal(r3['labels'], r2['labels'])
+
+
+def test_device_tpfp_state_matches_host_accumulation():
+    """tfe.TpFpDeviceState (records appended on the device, one copy at the end) against tfe.streaming_tp_fp_arrays
+    (the reference's per-batch host accumulation, tf_extended/metrics.py:133-206): identical records in identical
+    order for every class over several batches of different sizes, identical AP; zero scores and neither-TP-nor-FP
+    entries are dropped; a too small buffer is reported."""
+    need_cuda()
+    import torch
+    import ron_tensorflow_b200.tf_extended as tfe
+    rng = np.random.Generator(np.random.PCG64(11))
+    C = 7
+    dev_state = tfe.TpFpDeviceState(C, capacity=1 << 16)
+    host_state = None
+    for B, M in ((3, 40), (5, 40), (1, 17), (4, 200)):
+        sc = rng.uniform(0, 1, size=(B, C - 1, M)).astype(np.float32)
+        sc[rng.uniform(size=sc.shape) < 0.15] = 0.
+        sc[rng.uniform(size=sc.shape) < 0.05] = 1e-4                 # exactly at the filter's bound: dropped (strict >)
+        tp = rng.uniform(size=sc.shape) < 0.3
+        fp = (~tp) & (rng.uniform(size=sc.shape) < 0.6)
+        ng = rng.integers(0, 5, size=(B, C - 1)).astype(np.int64)
+        d = [torch.from_numpy(x).cuda() for x in (ng, tp, fp, sc)]
+        dev_state.update(*d)
+        _, host_state = tfe.streaming_tp_fp_arrays({c: ng[:, c - 1] for c in range(1, C)}, {c: tp[:, c - 1] for c in range(1, C)},
+                                                   {c: fp[:, c - 1] for c in range(1, C)}, {c: sc[:, c - 1] for c in range(1, C)},
+                                                   state=host_state)
+    got = tfe.gather_tp_fp(dev_state, C)                              # no process group: the local state on the host
+    for c in range(1, C):
+        assert got[c].n_gt == host_state[c].n_gt
+        eq(got[c].scores, host_state[c].scores, 'scores of class %d' % c)
+        eq(got[c].tp, host_state[c].tp, 'tp')
+        eq(got[c].fp, host_state[c].fp, 'fp')
+        pa, ra = tfe.precision_recall(*got[c].value())
+        pb, rb = tfe.precision_recall(*host_state[c].value())
+        assert tfe.average_precision_voc07(pa, ra) == tfe.average_precision_voc07(pb, rb)
+    assert int(dev_state.count_tensor().item()) == sum(host_state[c].scores.shape[0] for c in range(1, C))
+    small = tfe.TpFpDeviceState(C, capacity=16)
+    small.update(*d)
+    with pytest.raises(RuntimeError):
+        small.to_host()
