@@ -98,9 +98,9 @@ class TpFpDeviceState(object):
     @staticmethod
     def _split(records, n_gt, num_classes):
         """host records (int64 array in arrival order) -> dict class -> TpFpAccumulator (stable per class)."""
-        meta = (records & 0xffffffff).astype(np.uint32)
-        scores = (records >> 32).astype(np.uint32).view(np.float32)
-        cls = (meta >> 8).astype(np.uint16 if num_classes <= 65536 else np.int64)
+        w = np.ascontiguousarray(records).view(np.uint32).reshape(-1, 2)      # little endian: (meta, score bits)
+        meta, scores = w[:, 0].copy(), w[:, 1].copy().view(np.float32)
+        cls = (meta >> 8).astype(np.uint8 if num_classes <= 256 else (np.uint16 if num_classes <= 65536 else np.int64))
         order = np.argsort(cls, kind='stable')                    # radix sort for small integers: O(n)
         bounds = np.concatenate([[0], np.cumsum(np.bincount(cls, minlength=num_classes - 1))])
         scores, meta = scores[order], meta[order]
