@@ -543,6 +543,30 @@ def run_ours(args):
         h_s, h_b = h_ss[0], h_bs[0]
         del d_sets
 
+        # ---- the reference's call sequence verbatim (eval_ron_network.py:226-236): bboxes_decode per layer, the objectness
+        # gate as the caller writes it (framework ops on the whole prediction tensors), then detected_bboxes on dicts
+        def refseq_step():
+            localisations = net.bboxes_decode(d_loc, anchors)
+            filtered = [(o.unsqueeze(-1) > 0.03).float() * p_ for o, p_ in zip(d_obj, d_pred)]
+            return net.detected_bboxes(filtered, localisations, select_threshold=0.01, nms_threshold=POST_THR,
+                                       clipping_bbox=[0., 0., 1., 1.], top_k=POST_K, keep_top_k=POST_M)
+
+        rs_, rb_ = refseq_step()
+        if not (torch.equal(torch.stack([rs_[c] for c in range(1, N_CLASSES)], 1), res['s']) and
+                torch.equal(torch.stack([rb_[c] for c in range(1, N_CLASSES)], 1), res['b'])):
+            raise RuntimeError('bench: the reference call sequence and RONNet.detect disagree')
+        del rs_, rb_
+        barrier()
+        ms_seq = timed_steps(torch, refseq_step, max(4, args.steps // 2), 3)
+        seq_launches = timed_steps.launches
+        barrier()
+        refseq = {'metric': 'images/sec (bboxes_decode + caller-side objectness gate + detected_bboxes on dicts)',
+                  'value': world * POST_B * 1e3 / float(np.mean(ms_seq)), 'unit': 'images/s', 'ms_per_step': float(np.mean(ms_seq)),
+                  'vs_fused_detect': float(np.mean(ms_seq)) / float(np.mean(ms_p)), 'gpu_launches': seq_launches,
+                  'config': {'workload': 'eval_ron_network.py:226-236 as written, batch %d: 4 decode launches, the gate as 3 framework '
+                                         'ops per layer over the 457 MB of class scores (caller code, not libronk), then the fused '
+                                         'select / top-k and NMS kernels behind detected_bboxes; results equal RONNet.detect' % POST_B}}
+
         # VOC TP/FP records of ONE batch per rank: appended on the device, gathered ONCE with NCCL, AP on rank 0
         # (the same measurement as round 1's tpfp_gather: 1 batch per rank)
         n_gt, tp, fp = res['tpfp']
@@ -672,6 +696,7 @@ def run_ours(args):
                             'note': 'one batch per rank, records appended on the device (tfe.TpFpDeviceState), host clock around '
                                     'tfe.gather_tp_fp incl. the copy of all records to the host'},
             'eval_loop': eval_loop,
+            'reference_call_sequence': refseq,
         }
     # ---------------------------------------------------------------- next row: ron_eval.py single image
     roneval = None

@@ -58,6 +58,8 @@ extern "C" {
 typedef struct ronk_anchors ronk_anchors_t;
 
 int ronk_version(void);
+/* id of the CUDA-graph capture `stream` takes part in, 0 when it is not capturing (host-side helper of the bindings) */
+int ronk_stream_capture_id(void* stream, unsigned long long* out_id);
 const char* ronk_last_error(void);
 
 /* ------------------------------------------------------------------ anchors
@@ -239,6 +241,13 @@ int ronk_flaten_predict(const float* const* pred_layers_host, const float* const
                         float* out_scores, int64_t* out_labels, uint8_t* out_mask, void* stream);
 int ronk_filter_boxes_mask(const float* boxes, int n, float min_size, uint8_t* out_mask, void* stream);
 int ronk_minsize_mask(const float* boxes, int n, float min_size, uint8_t* out_mask, void* stream);
+/* RONNet.bboxes_filter_min (nets/ron_vgg_320.py:196-233) for S rows at once (all classes x images of the dict form):
+ * ronk_filter_min_count gives, per row, how many boxes have width > min_size and height > min_size; with the padded
+ * width = max(max count, top_k) known, ronk_filter_min_write writes the survivors of every row in order, zero-padded
+ * (tf.boolean_mask + pad_axis).  scores [S,N], boxes [S,N,4] -> out_scores [S,width], out_boxes [S,width,4]. */
+int ronk_filter_min_count(const float* boxes, int S, int N, float min_size, int32_t* out_counts, void* stream);
+int ronk_filter_min_write(const float* scores, const float* boxes, int S, int N, float min_size, int width,
+                          float* out_scores, float* out_boxes, void* stream);
 int ronk_rowmax_mask(const float* scores, int n, int C, float threshold, float* out_max, uint8_t* out_mask,
                      void* stream);
 size_t ronk_compact_workspace_bytes(int n);
@@ -294,6 +303,14 @@ int ronk_smooth_l1(const float* pred, const float* target, long long count, floa
                    float outside_weight, double sigma, float* out, void* stream);
 int ronk_localization_loss(const float* localisations, const float* glocalisations, const uint8_t* cls_positive,
                            long long n, double sigma, float beta, float* out_loss, void* ws, void* stream);
+/* Gradients of the two differentiable pieces (the reference differentiates the localisation term w.r.t. the network's
+ * `localisations`; `glocalisations` is wrapped in tf.stop_gradient, nets/ron_vgg_320.py:760): d SmoothL1 / d pred
+ * times grad_out element-wise, and d ronk_localization_loss / d localisations times the scalar *grad_out (device). */
+int ronk_smooth_l1_backward(const float* pred, const float* target, const float* grad_out, long long count,
+                            float inside_weight, float outside_weight, double sigma, float* grad_pred, void* stream);
+int ronk_localization_loss_backward(const float* localisations, const float* glocalisations, const uint8_t* cls_positive,
+                                    long long n, double sigma, float beta, const float* grad_out,
+                                    float* grad_localisations, void* ws, void* stream);
 
 /* ------------------------------------------- nets/np_methods.py (the notebooks' NumPy post-process)
  * (decode / sort / resize reuse ronk_decode, ronk_sort_topk, ronk_bboxes_resize)

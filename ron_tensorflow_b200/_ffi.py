@@ -21,6 +21,7 @@ SIGNATURES = {
     'ronk_version': (c_int, []),
     'ronk_last_error': (ctypes.c_char_p, []),
     'ronk_launch_count': (c_longlong, []),
+    'ronk_stream_capture_id': (c_int, [c_void_p, P(ctypes.c_ulonglong)]),
     'ronk_anchors_create': (c_int, [c_int, c_int, c_int, c_int, P(c_int), P(c_double), P(c_int), P(c_double),
                                     P(c_int), P(c_double), c_double, P(c_int), P(c_void_p)]),
     'ronk_anchors_create_flat': (c_int, [c_int, c_int, c_int, P(c_float), P(c_int), P(c_void_p)]),
@@ -59,6 +60,8 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     'ronk_filter_boxes_mask': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
     'ronk_minsize_mask': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    'ronk_filter_min_count': (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'ronk_filter_min_write': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
     'ronk_rowmax_mask': (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'ronk_compact_workspace_bytes': (c_size_t, [c_int]),
     'ronk_compact_indices': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -91,6 +94,9 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_void_p, c_void_p,
                                 c_void_p]),
     'ronk_smooth_l1': (c_int, [c_void_p, c_void_p, c_longlong, c_float, c_float, c_double, c_void_p, c_void_p]),
+    'ronk_smooth_l1_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_double, c_void_p, c_void_p]),
+    'ronk_localization_loss_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_float, c_void_p, c_void_p,
+                                                c_void_p, c_void_p]),
     'ronk_localization_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_float, c_void_p, c_void_p,
                                        c_void_p]),
     'ronk_tpfp_match': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,

@@ -36,6 +36,9 @@ def as_cuda(x, dtype, device=None):
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
     if not t.is_cuda:
         t = t.to(device or 'cuda', non_blocking=True)
+    elif device is not None and t.device != torch.device(device):
+        # a tensor of another GPU must not reach a kernel launched on `device` (illegal address / silent peer access)
+        t = t.to(device, non_blocking=True)
     if t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()
@@ -172,18 +175,67 @@ class AnchorSet(object):
         return out
 
 
-# workspaces are cached per (device, stream, shape): the encode workspace must stay zeroed
-# between calls (the kernels restore it), torch.zeros provides the initial state.
+# Scratch workspaces are cached per (kind, device, stream), sized by capacity (rounded up to a power of two, so a
+# smaller last batch reuses the buffer of the full ones); the encode / loss workspaces, which must be zero between calls
+# (the kernels restore them; torch.zeros provides the initial state), per exact shape.  Least-recently-used entries are
+# evicted beyond _WS_MAX.
+# During CUDA-graph capture the cache is bypassed: a buffer allocated while capturing belongs to that graph's private
+# pool and its zero-fill is a node of that graph -- handing it to a second capture would replay kernels on a workspace
+# nobody zeroed.  Every capture therefore gets its own workspace, zeroed by a libronk launch inside the capture.
 _ws_cache = {}
+_WS_MAX = 24
+_capture_ws = {}          # (capture id, kind, device, stream, shape) -> workspace of that capture (graphs replay on them)
 
 
-def _workspace(kind, nbytes, zero, device):
-    key = (kind, device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
-    t = _ws_cache.get(key)
-    if t is None:
-        n = (int(nbytes) + 7) // 8
-        t = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=torch.int64, device=device)
-        _ws_cache[key] = t
+def _capture_id():
+    cid = ctypes.c_ulonglong(0)
+    _ffi.check(_ffi.lib().ronk_stream_capture_id(_stream(), ctypes.byref(cid)))
+    return int(cid.value)
+
+
+def _zero_ws(kind, t, B=None, G=None):
+    L = _ffi.lib()
+    with torch.cuda.device(t.device):
+        if kind == 'enc':
+            _ffi.check(L.ronk_encode_workspace_init(_ptr(t), int(B), int(G), _stream()))
+        elif kind == 'loss':
+            _ffi.check(L.ronk_loss_workspace_init(_ptr(t), _stream()))
+
+
+def _workspace(kind, nbytes, zero, device, init_args=None):
+    nbytes = max(int(nbytes), 8)
+    cid = _capture_id()
+    if cid:
+        # one workspace per (capture, stream, shape): zeroed by a libronk launch that is a node of THIS graph, then
+        # reused by the later calls of the same capture on that stream (every kernel leaves it zeroed)
+        key = (cid, kind, device.index, torch.cuda.current_stream(device).cuda_stream, nbytes, tuple(init_args or ()))
+        t = _capture_ws.get(key)
+        if t is None:
+            t = torch.empty(((nbytes + 7) // 8,), dtype=torch.int64, device=device)
+            if zero:
+                _zero_ws(kind, t, *(init_args or ()))
+            if len(_capture_ws) > 256:
+                for k in [k for k in _capture_ws if k[0] != cid][:128]:
+                    del _capture_ws[k]                      # (their graphs keep the memory pool alive, not the tensors)
+            _capture_ws[key] = t
+        return t
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if zero:
+        # a zero-between-calls workspace is laid out by its exact shape: one buffer per shape (LRU-bounded)
+        cap = (nbytes + 7) // 8 * 8
+        key = (kind, device.index, stream, cap, tuple(init_args or ()))
+    else:
+        cap = 1 << (nbytes - 1).bit_length()
+        key = (kind, device.index, stream)
+    hit = _ws_cache.get(key)
+    if hit is not None and hit.numel() * 8 >= nbytes:
+        _ws_cache[key] = _ws_cache.pop(key)                # most recently used last
+        return hit
+    t = (torch.zeros if zero else torch.empty)((cap // 8,), dtype=torch.int64, device=device)
+    _ws_cache.pop(key, None)
+    _ws_cache[key] = t
+    while len(_ws_cache) > _WS_MAX:
+        _ws_cache.pop(next(iter(_ws_cache)))
     return t
 
 
@@ -212,7 +264,7 @@ def match_encode(anchors, gt_boxes, gt_labels, gt_counts, positive_threshold=0.5
     objn = (o.get('objness') if o.get('objness') is not None else
             torch.empty((B, N), dtype=torch.int32, device=dev)) if want_objness else None
     L = _ffi.lib()
-    ws = _workspace('enc', L.ronk_encode_workspace_bytes(B, G), True, dev)
+    ws = _workspace('enc', L.ronk_encode_workspace_bytes(B, G), True, dev, (B, G))
     flags = (0 if ignore_between else _ffi.MATCH_NO_IGNORE_BETWEEN) | (0 if gt_max_first else _ffi.MATCH_NO_GT_MAX_FIRST)
     with torch.cuda.device(dev):
         rc = L.ronk_match_encode(anchors.handle, _ptr(gb), _ptr(gl), _ptr(gc), B, G, float(positive_threshold),
@@ -505,6 +557,35 @@ def minsize_mask(boxes, min_size):
     return mask
 
 
+def filter_min_rows(scores, boxes, top_k, min_size):
+    """RONNet.bboxes_filter_min on rows: scores [S,N], boxes [S,N,4] -> [S,width], [S,width,4] with
+    width = max(longest surviving row, top_k), plus the per-row survivor counts (host).  Two launches and ONE read-back
+    (the per-row counts decide the width)."""
+    s = as_cuda(scores, torch.float32)
+    b = as_cuda(boxes, torch.float32, s.device)
+    if s.dim() != 2 or b.shape != s.shape + (4,):
+        raise ValueError('expected scores [S,N] and boxes [S,N,4]')
+    S, N = int(s.shape[0]), int(s.shape[1])
+    counts = torch.empty((S,), dtype=torch.int32, device=s.device)
+    L = _ffi.lib()
+    with torch.cuda.device(s.device):
+        _ffi.check(L.ronk_filter_min_count(_ptr(b), S, N, float(min_size), _ptr(counts), _stream()))
+    counts_host = counts.cpu().numpy()                      # the one read-back: the output width is data dependent
+    width = max(int(counts_host.max()), int(top_k))
+    os_ = torch.empty((S, width), dtype=torch.float32, device=s.device)
+    ob = torch.empty((S, width, 4), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        _ffi.check(L.ronk_filter_min_write(_ptr(s), _ptr(b), S, N, float(min_size), width, _ptr(os_), _ptr(ob), _stream()))
+    return os_, ob, counts_host
+
+
+def stack_classes(d, keys, dtype=torch.float32):
+    """dict class -> [B, ...] tensors -> one [C, B, ...] tensor (a single torch.stack: the dict forms of the
+    reference's functions then cost one launch instead of one per class)."""
+    ts = [as_cuda(d[k], dtype) for k in keys]
+    return torch.stack(ts, 0)
+
+
 def rowmax_mask(scores, threshold):
     s = as_cuda(scores, torch.float32)
     n, C = int(s.shape[0]), int(s.shape[1])
@@ -709,12 +790,7 @@ def loss_masks(gclasses, objness_pred, rand_objness, rand_cls, objness_threshold
     return fo.view(torch.bool), lab, cp.view(torch.bool), fc.view(torch.bool), cnt, (loss[0] if loss is not None else None)
 
 
-def smooth_l1(bbox_pred, bbox_targets, inside_weight=1., outside_weight=1., sigma=1.):
-    """nets/custom_layers.py:31-50, element-wise."""
-    a = as_cuda(bbox_pred, torch.float32)
-    b = as_cuda(bbox_targets, torch.float32, a.device)
-    if a.shape != b.shape:
-        raise ValueError('bbox_pred and bbox_targets must have the same shape')
+def _smooth_l1_forward(a, b, inside_weight, outside_weight, sigma):
     out = torch.empty_like(a)
     with torch.cuda.device(a.device):
         _ffi.check(_ffi.lib().ronk_smooth_l1(_ptr(a), _ptr(b), a.numel(), float(inside_weight), float(outside_weight),
@@ -722,15 +798,38 @@ def smooth_l1(bbox_pred, bbox_targets, inside_weight=1., outside_weight=1., sigm
     return out
 
 
-def localization_loss(localisations, glocalisations, cls_positive_mask, sigma=3., beta=1. / 3):
-    """nets/ron_vgg_320.py:760-764 -> float32 scalar tensor on the device."""
-    a = as_cuda(localisations, torch.float32).reshape(-1, 4)
-    b = as_cuda(glocalisations, torch.float32, a.device).reshape(-1, 4)
-    m = cls_positive_mask
-    m = (m.view(torch.uint8) if isinstance(m, torch.Tensor) and m.dtype == torch.bool else as_cuda(m, torch.uint8, a.device))
-    m = m.to(a.device).reshape(-1).contiguous()
-    if not (a.shape == b.shape and m.numel() == a.shape[0]):
-        raise ValueError('localisations / glocalisations [n,4] and cls_positive_mask [n] expected')
+class _SmoothL1Fn(torch.autograd.Function):
+    """modified_smooth_l1 with its gradient (ronk_smooth_l1_backward): d/d pred, and minus that for the targets."""
+
+    @staticmethod
+    def forward(ctx, a, b, inside_weight, outside_weight, sigma):
+        ctx.save_for_backward(a, b)
+        ctx.cfg = (float(inside_weight), float(outside_weight), float(sigma))
+        return _smooth_l1_forward(a, b, inside_weight, outside_weight, sigma)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b = ctx.saved_tensors
+        g = grad_out.contiguous().to(torch.float32)
+        ga = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            _ffi.check(_ffi.lib().ronk_smooth_l1_backward(_ptr(a), _ptr(b), _ptr(g), a.numel(), ctx.cfg[0], ctx.cfg[1], ctx.cfg[2],
+                                                          _ptr(ga), _stream()))
+        return ga, (-ga if ctx.needs_input_grad[1] else None), None, None, None
+
+
+def smooth_l1(bbox_pred, bbox_targets, inside_weight=1., outside_weight=1., sigma=1.):
+    """nets/custom_layers.py:31-50, element-wise; differentiable w.r.t. both tensors."""
+    a = as_cuda(bbox_pred, torch.float32)
+    b = as_cuda(bbox_targets, torch.float32, a.device)
+    if a.shape != b.shape:
+        raise ValueError('bbox_pred and bbox_targets must have the same shape')
+    if a.requires_grad or b.requires_grad:
+        return _SmoothL1Fn.apply(a, b, inside_weight, outside_weight, sigma)
+    return _smooth_l1_forward(a, b, inside_weight, outside_weight, sigma)
+
+
+def _localization_loss_forward(a, b, m, sigma, beta):
     out = torch.empty((1,), dtype=torch.float32, device=a.device)
     L = _ffi.lib()
     ws = _workspace('loss', L.ronk_loss_workspace_bytes(), True, a.device)
@@ -738,6 +837,43 @@ def localization_loss(localisations, glocalisations, cls_positive_mask, sigma=3.
         _ffi.check(L.ronk_localization_loss(_ptr(a), _ptr(b), _ptr(m), int(a.shape[0]), float(sigma), float(beta), _ptr(out),
                                             _ptr(ws), _stream()))
     return out[0]
+
+
+class _LocLossFn(torch.autograd.Function):
+    """The localisation term with its gradient w.r.t. the network's localisations (the reference wraps the targets in
+    tf.stop_gradient, nets/ron_vgg_320.py:760: no gradient flows to glocalisations)."""
+
+    @staticmethod
+    def forward(ctx, a, b, m, sigma, beta):
+        ctx.save_for_backward(a, b, m)
+        ctx.cfg = (float(sigma), float(beta))
+        return _localization_loss_forward(a, b, m, sigma, beta)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b, m = ctx.saved_tensors
+        g = grad_out.reshape(1).contiguous().to(torch.float32)
+        ga = torch.empty_like(a)
+        L = _ffi.lib()
+        ws = _workspace('loss', L.ronk_loss_workspace_bytes(), True, a.device)
+        with torch.cuda.device(a.device):
+            _ffi.check(L.ronk_localization_loss_backward(_ptr(a), _ptr(b), _ptr(m), int(a.shape[0]), ctx.cfg[0], ctx.cfg[1],
+                                                         _ptr(g), _ptr(ga), _ptr(ws), _stream()))
+        return ga, None, None, None, None
+
+
+def localization_loss(localisations, glocalisations, cls_positive_mask, sigma=3., beta=1. / 3):
+    """nets/ron_vgg_320.py:760-764 -> float32 scalar tensor on the device; differentiable w.r.t. ``localisations``."""
+    a = as_cuda(localisations, torch.float32).reshape(-1, 4)
+    b = as_cuda(glocalisations, torch.float32, a.device).reshape(-1, 4)
+    m = cls_positive_mask
+    m = (m.view(torch.uint8) if isinstance(m, torch.Tensor) and m.dtype == torch.bool else as_cuda(m, torch.uint8, a.device))
+    m = m.to(a.device).reshape(-1).contiguous()
+    if not (a.shape == b.shape and m.numel() == a.shape[0]):
+        raise ValueError('localisations / glocalisations [n,4] and cls_positive_mask [n] expected')
+    if a.requires_grad:
+        return _LocLossFn.apply(a, b.detach(), m, sigma, beta)
+    return _localization_loss_forward(a, b, m, sigma, beta)
 
 
 # ----------------------------------------------------------------------------- host-buffer encode (sparse D2H)

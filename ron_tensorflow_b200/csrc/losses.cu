@@ -208,6 +208,47 @@ __global__ void loc_loss_finish_kernel(const double* __restrict__ acc, float bet
     out[0] = acc[1] > 0. ? (float)((double)beta * (acc[0] / acc[1])) : 0.f;
 }
 
+// d SmoothL1 / d pred of one element (the comparison is a constant for the gradient, like tf.cast(tf.less(...)));
+// tf.abs has gradient sign(x), 0 at 0
+__device__ __forceinline__ float smooth_l1_grad(const SmoothL1& f, float pred, float target) {
+    const float x = f.in_w * (pred - target);
+    const float d = fabsf(x) < f.thr ? (x + x) * f.half_s2 : (x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f));
+    return f.out_w * d * f.in_w;
+}
+
+__global__ void __launch_bounds__(256)
+smooth_l1_backward_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ grad_out,
+                          long long count, SmoothL1 f, float* __restrict__ grad_pred) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) grad_pred[i] = grad_out[i] * smooth_l1_grad(f, pred[i], target[i]);
+}
+
+__global__ void __launch_bounds__(256)
+mask_count_kernel(const uint8_t* __restrict__ mask, long long n, double* __restrict__ acc) {
+    unsigned cnt = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cnt += mask[i] ? 1u : 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(acc, (double)cnt);
+}
+
+// d (beta * mean over the masked rows of the row sums) / d localisations, times the incoming scalar gradient
+__global__ void __launch_bounds__(256)
+loc_loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ gloc, const uint8_t* __restrict__ mask,
+                         long long n, SmoothL1 f, float beta, const double* __restrict__ acc, const float* __restrict__ grad_out,
+                         float4* __restrict__ grad_loc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mask[i] && acc[0] > 0.) {
+        const float s = grad_out[0] * (float)((double)beta / acc[0]);
+        const float4 a = loc[i], b = gloc[i];
+        g = make_float4(s * smooth_l1_grad(f, a.x, b.x), s * smooth_l1_grad(f, a.y, b.y), s * smooth_l1_grad(f, a.z, b.z),
+                        s * smooth_l1_grad(f, a.w, b.w));
+    }
+    grad_loc[i] = g;
+}
+
 static SmoothL1 make_smooth_l1(float inside_w, float outside_w, double sigma) {
     const double s2 = sigma * sigma;
     SmoothL1 f;
@@ -296,6 +337,40 @@ extern "C" int ronk_smooth_l1(const float* pred, const float* target, long long 
     smooth_l1_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         pred, target, count, make_smooth_l1(inside_weight, outside_weight, sigma), out);
     RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_smooth_l1_backward(const float* pred, const float* target, const float* grad_out, long long count,
+                                       float inside_weight, float outside_weight, double sigma, float* grad_pred, void* stream) {
+    RONK_REQUIRE(count >= 0 && sigma > 0. && (count == 0 || (pred && target && grad_out && grad_pred)), RONK_EINVAL,
+                 "ronk_smooth_l1_backward: bad argument");
+    if (count == 0) return RONK_OK;
+    smooth_l1_backward_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        pred, target, grad_out, count, make_smooth_l1(inside_weight, outside_weight, sigma), grad_pred);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_localization_loss_backward(const float* localisations, const float* glocalisations,
+                                               const uint8_t* cls_positive, long long n, double sigma, float beta,
+                                               const float* grad_out, float* grad_localisations, void* ws, void* stream) {
+    RONK_REQUIRE(n >= 0 && sigma > 0. && grad_out && ws && (n == 0 || (localisations && glocalisations && cls_positive && grad_localisations)),
+                 RONK_EINVAL, "ronk_localization_loss_backward: bad argument");
+    RONK_REQUIRE(((uintptr_t)localisations % 16) == 0 && ((uintptr_t)glocalisations % 16) == 0 &&
+                 ((uintptr_t)grad_localisations % 16) == 0 && ((uintptr_t)ws % 8) == 0, RONK_EINVAL,
+                 "ronk_localization_loss_backward: box pointers must be 16-byte aligned, ws 8-byte aligned");
+    if (n == 0) return RONK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* acc = (double*)((char*)ws + 48);
+    RONK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    mask_count_kernel<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(cls_positive, n, acc);
+    RONK_LAUNCHED();
+    loc_loss_backward_kernel<<<blocks, 256, 0, st>>>((const float4*)localisations, (const float4*)glocalisations, cls_positive, n,
+                                                     make_smooth_l1(1.f, 1.f, sigma), beta, acc, grad_out,
+                                                     (float4*)grad_localisations);
+    RONK_LAUNCHED();
+    RONK_CUDA(cudaMemsetAsync(acc, 0, 16, st));
     return RONK_OK;
 }
 

@@ -69,6 +69,69 @@ minsize_mask_kernel(const float4* __restrict__ boxes, int n, float min_size, uin
     mask[i] = ((b.w - b.y) > min_size && (b.z - b.x) > min_size) ? 1 : 0;
 }
 
+// RONNet.bboxes_filter_min for many rows at once (every (class, image) row of the dict form): a CTA per row counts the
+// boxes that pass, then (second launch, once the padded width is known) writes them in order, zero-padded.
+__global__ void __launch_bounds__(256)
+filter_min_count_kernel(const float4* __restrict__ boxes, int N, float min_size, int* __restrict__ counts) {
+    __shared__ int s_w[8];
+    const float4* row = boxes + (size_t)blockIdx.x * N;
+    int c = 0;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        const float4 b = row[i];
+        c += ((b.w - b.y) > min_size && (b.z - b.x) > min_size) ? 1 : 0;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+filter_min_write_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes, int N, float min_size, int width,
+                        float* __restrict__ out_scores, float4* __restrict__ out_boxes) {
+    __shared__ int s_w[8];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* srow = scores + (size_t)blockIdx.x * N;
+    const float4* brow = boxes + (size_t)blockIdx.x * N;
+    float* os = out_scores + (size_t)blockIdx.x * width;
+    float4* ob = out_boxes + (size_t)blockIdx.x * width;
+    int pos = 0;
+    for (int i0 = 0; i0 < N; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool keep = false;
+        if (i < N) {
+            b = brow[i];
+            keep = (b.w - b.y) > min_size && (b.z - b.x) > min_size;
+        }
+        const unsigned m = __ballot_sync(full, keep);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            before += (w < warp) ? s_w[w] : 0;
+            all += s_w[w];
+        }
+        if (keep) {
+            const int o = pos + before + __popc(m & ((1u << lane) - 1u));
+            os[o] = srow[i];
+            ob[o] = b;
+        }
+        pos += all;
+    }
+    for (int o = pos + threadIdx.x; o < width; o += 256) {      // pad_axis (tensors.py:59-86)
+        os[o] = 0.f;
+        ob[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 rowmax_mask_kernel(const float* __restrict__ scores, int n, int C, float thr, float* __restrict__ out,
                    uint8_t* __restrict__ mask) {
@@ -311,6 +374,26 @@ extern "C" int ronk_minsize_mask(const float* boxes, int n, float min_size, uint
     if (n == 0) return RONK_OK;
     RONK_REQUIRE(boxes && out_mask && ((uintptr_t)boxes % 16) == 0, RONK_EINVAL, "ronk_minsize_mask: bad argument");
     minsize_mask_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, n, min_size, out_mask);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_filter_min_count(const float* boxes, int S, int N, float min_size, int32_t* out_counts, void* stream) {
+    RONK_REQUIRE(boxes && out_counts && S >= 1 && N >= 1 && ((uintptr_t)boxes % 16) == 0, RONK_EINVAL,
+                 "ronk_filter_min_count: bad argument");
+    filter_min_count_kernel<<<S, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, N, min_size, out_counts);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+extern "C" int ronk_filter_min_write(const float* scores, const float* boxes, int S, int N, float min_size, int width,
+                                     float* out_scores, float* out_boxes, void* stream) {
+    RONK_REQUIRE(scores && boxes && out_scores && out_boxes && S >= 1 && N >= 1 && width >= 1, RONK_EINVAL,
+                 "ronk_filter_min_write: bad argument");
+    RONK_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)out_boxes % 16) == 0, RONK_EINVAL,
+                 "ronk_filter_min_write: box pointers must be 16-byte aligned");
+    filter_min_write_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(scores, (const float4*)boxes, N, min_size, width, out_scores,
+                                                                (float4*)out_boxes);
     RONK_LAUNCHED();
     return RONK_OK;
 }

@@ -26,8 +26,14 @@ RONParams = namedtuple('SSDParameters', ['img_shape', 'num_classes', 'no_annotat
 
 class AnchorList(list):
     """The list of per-layer (y, x, h, w) NumPy arrays the reference returns, carrying the
-    device-side anchor handle so bboxes_encode / bboxes_decode need no second upload."""
+    device-side anchor handle so bboxes_encode / bboxes_decode need no second upload.  ``fingerprint`` is a hash
+    of the arrays at creation: a list whose arrays were edited afterwards no longer matches its handle and is treated
+    as plain arrays."""
     anchor_set = None
+    fingerprint = None
+
+
+_fingerprint = ssd_common.fingerprint
 
 
 def _anchor_set(kind, img_shape, layers_shape, anchor_sizes, anchor_ratios, anchor_steps, offset, borders):
@@ -49,6 +55,7 @@ def ron_anchors_all_layers(img_shape, layers_shape, anchor_sizes, anchor_ratios,
                     allowed_borders)
     out = AnchorList([tuple(v.astype(dtype) for v in t) for t in a.as_reference_list()])
     out.anchor_set = a
+    out.fingerprint = _fingerprint(out)
     return out
 
 
@@ -84,18 +91,25 @@ class RONNet(object):
         return self._sets[key]
 
     def _resolve(self, anchors):
-        a = getattr(anchors, 'anchor_set', None)
-        if a is None:
-            a = self._set_for(self.params.img_shape)
-            if anchors is not None and len(anchors) != a.L:
-                raise IndexError('anchors: expected %d layers, got %d' % (a.L, len(anchors)))
-        return a
+        """The device handle to use for ``anchors``: the cached default set only when ``anchors`` is None; the handle
+        riding on a list RONNet.anchors returned, as long as its arrays are untouched; None for any other list of
+        (y, x, h, w) arrays -- the caller's values are then used as given (a content-hashed flat handle built by
+        nets.ssd_common), like the reference, which always computes with the anchors it is handed."""
+        if anchors is None:
+            return self._set_for(self.params.img_shape)
+        return ssd_common.handle_of(anchors)
+
+    def _resolve_set(self, anchors, allowed_borders):
+        """Like _resolve, but always a handle (for the batched forms that have no array path)."""
+        a = self._resolve(anchors)
+        return a if a is not None else ssd_common.anchor_set_from_arrays(anchors, self.params.img_shape, allowed_borders)
 
     def anchors(self, img_shape, dtype=np.float32):
         """reference: nets/ron_vgg_320.py:162-171."""
         a = self._set_for(img_shape)
         out = AnchorList([tuple(v.astype(dtype) for v in t) for t in a.as_reference_list()])
         out.anchor_set = a
+        out.fingerprint = _fingerprint(out)
         return out
 
     # ------------------------------------------------------------------- encode
@@ -113,15 +127,15 @@ class RONNet(object):
                             ignore_threshold=0.3, want_matched=False, want_objness=False):
         """Batched form: labels [B,Gmax] int64, bboxes [B,Gmax,4], counts [B] int32 ->
         dict(labels [B,N], loc [B,N,4], scores [B,N], matched?, objness?)."""
-        return core.match_encode(self._resolve(anchors), bboxes, labels, counts, positive_threshold,
-                                 ignore_threshold, self.params.prior_scaling, want_matched=want_matched,
+        return core.match_encode(self._resolve_set(anchors, self.params.allowed_borders), bboxes, labels, counts,
+                                 positive_threshold, ignore_threshold, self.params.prior_scaling, want_matched=want_matched,
                                  want_objness=want_objness)
 
     def host_encoder(self, batch, g_max, anchors=None, slots=2, positive_threshold=0.5, ignore_threshold=0.3, **kw):
         """Batched encode for ground truth and targets in HOST memory (the reference encodes on the CPU inside its
         input pipeline): see core.HostEncoder -- submit(slot, boxes, labels, counts) / collect(slot)."""
-        return core.HostEncoder(self._resolve(anchors), batch, g_max, slots, positive_threshold, ignore_threshold,
-                                self.params.prior_scaling, **kw)
+        return core.HostEncoder(self._resolve_set(anchors, self.params.allowed_borders), batch, g_max, slots,
+                                positive_threshold, ignore_threshold, self.params.prior_scaling, **kw)
 
     # ------------------------------------------------------------------- decode
     def bboxes_decode(self, feat_localizations, anchors, scope='ssd_bboxes_decode'):
@@ -135,25 +149,19 @@ class RONNet(object):
         therefore only accepts batch 1 (:221); here every image of the batch is filtered and the
         result is padded to the longest row."""
         if isinstance(scores, dict) or isinstance(bboxes, dict):
-            d_scores, d_bboxes = {}, {}
-            for c in scores.keys():
-                d_scores[c], d_bboxes[c] = self.bboxes_filter_min(scores[c], bboxes[c], top_k, minsize=minsize)
-            return d_scores, d_bboxes
+            # all classes and images in two launches and one read-back.  Per class the reference pads to
+            # max(its own survivors, top_k); rows are cut back to that width, so every class has the reference's shape
+            keys = list(scores.keys())
+            s, b = core.stack_classes(scores, keys), core.stack_classes(bboxes, keys)
+            C, B = int(s.shape[0]), int(s.shape[1])
+            os_, ob, counts = core.filter_min_rows(s.reshape(C * B, -1), b.reshape(C * B, -1, 4), top_k, minsize)
+            os_, ob = os_.view(C, B, -1), ob.view(C, B, -1, 4)
+            widths = [max(int(top_k), int(v)) for v in counts.reshape(C, B).max(1)]
+            return ({c: os_[i, :, :widths[i]] for i, c in enumerate(keys)},
+                    {c: ob[i, :, :widths[i]] for i, c in enumerate(keys)})
         s = core.as_cuda(scores, torch.float32)
         b = core.as_cuda(bboxes, torch.float32, s.device)
-        # per image: size mask kernel -> order-preserving compaction -> row gather (dynamic shapes, like
-        # tf.boolean_mask); the fused path (detected_bboxes / detect) never materialises this tensor --
-        # the size test lives inside the select kernel.
-        kept = []
-        for i in range(s.shape[0]):
-            idx = core.compact_indices(core.minsize_mask(b[i], np.float32(minsize)))
-            kept.append((core.gather_rows(s[i].contiguous(), idx), core.gather_rows(b[i].contiguous(), idx)))
-        width = max(max(int(k[0].shape[0]) for k in kept), int(top_k))          # pad_axis to >= top_k (:230-231)
-        os_ = torch.zeros((s.shape[0], width), dtype=torch.float32, device=s.device)
-        ob = torch.zeros((s.shape[0], width, 4), dtype=torch.float32, device=s.device)
-        for i, (ks, kb) in enumerate(kept):
-            os_[i, :ks.shape[0]] = ks
-            ob[i, :ks.shape[0]] = kb
+        os_, ob, _ = core.filter_min_rows(s, b, top_k, minsize)
         return os_, ob
 
     # ------------------------------------------------------------------ detect
@@ -229,12 +237,18 @@ def ron_loss_masks(gclasses, objness_pred, rand_objness=None, rand_cls=None, obj
         if isinstance(x, (list, tuple)):
             return torch.cat([core.as_cuda(t, torch.float32).reshape(-1, 4) for t in x], 0)
         return core.as_cuda(x, torch.float32).reshape(-1, 4)
+    fl, fg = flat4(localisations), flat4(glocalisations)
+    # the fused launch gives the VALUE of the localisation term; when the localisations take part in autograd the
+    # term is computed by the differentiable form instead (one more launch), so loss.backward() reaches them
+    need_grad = fl is not None and fl.requires_grad
     fo, lab, cp, fc, cnt, loss = core.loss_masks(g, o, flat(rand_objness, torch.float32), flat(rand_cls, torch.float32),
-                                                 objness_threshold, negative_ratio, flat4(localisations),
-                                                 flat4(glocalisations), 3., beta)
+                                                 objness_threshold, negative_ratio, None if need_grad else fl,
+                                                 None if need_grad else fg, 3., beta)
     out = dict(final_neg_mask_objness=fo, objness_pred_label=lab, cls_positive_mask=cp,
                final_cls_neg_mask_objness=fc, counts=cnt)
-    if loss is not None:
+    if need_grad:
+        out['localization_loss'] = core.localization_loss(fl, fg, cp, 3., beta)
+    elif loss is not None:
         out['localization_loss'] = loss
     return out
 

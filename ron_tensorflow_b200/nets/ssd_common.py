@@ -51,6 +51,35 @@ def _anchors_to_flat(anchors):
     return flat, sizes, shapes
 
 
+def fingerprint(anchors):
+    """Hash of a list of per-layer (y, x, h, w) arrays."""
+    h = hashlib.sha1()
+    for t in anchors:
+        for v in t:
+            a = np.ascontiguousarray(np.asarray(v))
+            h.update(str(a.shape).encode() + str(a.dtype).encode() + a.tobytes())
+    return h.hexdigest()
+
+
+def handle_of(anchors):
+    """The device handle riding on a list RONNet.anchors / SSDNet.anchors returned -- only while its arrays are the
+    ones the handle was built from (the fingerprint taken at creation still matches); None otherwise."""
+    a = getattr(anchors, 'anchor_set', None)
+    if a is not None and getattr(anchors, 'fingerprint', None) == fingerprint(anchors):
+        return a
+    return None
+
+
+def anchor_set_from_arrays(anchors, img_shape, allowed_borders):
+    """Handle for a caller-supplied list of per-layer (y, x, h, w) arrays (reference :371-402), cached by content."""
+    flat, sizes, _ = _anchors_to_flat(anchors)
+    if allowed_borders is not None and len(allowed_borders) != len(sizes):
+        raise IndexError('allowed_borders must have one entry per layer')
+    borders = None if allowed_borders is None else \
+        np.concatenate([np.full(n, b, np.int32) for n, b in zip(sizes, allowed_borders)])
+    return _flat_set(img_shape, flat, borders)
+
+
 # ----------------------------------------------------------------------------- IoU / matching
 def areas(bboxes):
     """reference :27-29.  [G,4] -> [G,1]."""
@@ -109,7 +138,7 @@ def tf_ssd_bboxes_encode(labels, bboxes, anchors, num_classes, img_shape, allowe
     Returns four lists over layers: labels flat [n_l], localisations [H,W,A,4], scores flat [n_l],
     anchor corner boxes [H,W,A,4].  (The reference only works for exactly 4 layers, :385-388;
     any number of layers is accepted here with identical results for 4.)"""
-    aset = _anchor_set if _anchor_set is not None else getattr(anchors, 'anchor_set', None)
+    aset = _anchor_set if _anchor_set is not None else handle_of(anchors)
     if aset is not None and aset.gen_params is not None:
         aset = aset.with_borders(allowed_borders)
         sizes = aset.layer_sizes
@@ -147,7 +176,7 @@ def tf_ssd_bboxes_decode_layer(feat_localizations, anchors_layer, prior_scaling=
 def tf_ssd_bboxes_decode(feat_localizations, anchors, prior_scaling=_PS, scope='ssd_bboxes_decode',
                          _anchor_set=None):
     """reference :477-498.  Lists over layers of [B,H,W,A,4]."""
-    aset = _anchor_set if _anchor_set is not None else getattr(anchors, 'anchor_set', None)
+    aset = _anchor_set if _anchor_set is not None else handle_of(anchors)
     if aset is None:
         return [tf_ssd_bboxes_decode_layer(feat_localizations[i], a, prior_scaling) for i, a in enumerate(anchors)]
     out = []

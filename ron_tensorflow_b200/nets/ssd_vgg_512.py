@@ -8,7 +8,7 @@ import torch
 
 from .. import core
 from . import ssd_common
-from .ron_vgg_320 import AnchorList, _nms_to_dicts
+from .ron_vgg_320 import AnchorList, _nms_to_dicts, _fingerprint
 
 # reference: nets/ssd_vgg_512.py:48-61
 SSDParams = namedtuple('SSDParameters', ['img_shape', 'num_classes', 'no_annotation_label', 'feat_layers',
@@ -28,6 +28,7 @@ def ssd_anchors_all_layers(img_shape, layers_shape, anchor_sizes, anchor_ratios,
     a = core.AnchorSet('ssd', img_shape, layers_shape, anchor_sizes, anchor_ratios, anchor_steps, offset, None)
     out = AnchorList([tuple(v.astype(dtype) for v in t) for t in a.as_reference_list()])
     out.anchor_set = a
+    out.fingerprint = _fingerprint(out)
     return out
 
 
@@ -64,14 +65,22 @@ class SSDNet(object):
         return self._sets[key]
 
     def _resolve(self, anchors):
-        a = getattr(anchors, 'anchor_set', None)
-        return a if a is not None else self._set_for(self.params.img_shape)
+        """See RONNet._resolve: the default handle only for None, the riding handle while the arrays are untouched,
+        otherwise None (the caller's arrays are used as given)."""
+        if anchors is None:
+            return self._set_for(self.params.img_shape)
+        return ssd_common.handle_of(anchors)
+
+    def _resolve_set(self, anchors, allowed_borders=None):
+        a = self._resolve(anchors)
+        return a if a is not None else ssd_common.anchor_set_from_arrays(anchors, self.params.img_shape, allowed_borders)
 
     def anchors(self, img_shape, dtype=np.float32):
         """reference: nets/ssd_vgg_512.py:150-159."""
         a = self._set_for(img_shape)
         out = AnchorList([tuple(v.astype(dtype) for v in t) for t in a.as_reference_list()])
         out.anchor_set = a
+        out.fingerprint = _fingerprint(out)
         return out
 
     def bboxes_encode(self, labels, bboxes, anchors, scope=None, positive_threshold=0.5, ignore_threshold=0.5,
@@ -88,7 +97,7 @@ class SSDNet(object):
 
     def bboxes_encode_batch(self, labels, bboxes, counts, anchors=None, positive_threshold=0.5,
                             ignore_threshold=0.5, want_matched=False, want_objness=False):
-        return core.match_encode(self._resolve(anchors), bboxes, labels, counts, positive_threshold,
+        return core.match_encode(self._resolve_set(anchors), bboxes, labels, counts, positive_threshold,
                                  ignore_threshold, self.params.prior_scaling, want_matched=want_matched,
                                  want_objness=want_objness)
 

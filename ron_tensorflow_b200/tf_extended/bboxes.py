@@ -25,10 +25,13 @@ def bboxes_sort(scores, bboxes, top_k=400, scope=None):
     """reference :60-101.  Batch x N scores / Batch x N x 4 boxes (or dicts of them) ->
     Batch x top_k, sorted by decreasing score, ties keep the lower index first."""
     if isinstance(scores, dict) or isinstance(bboxes, dict):
-        d_scores, d_bboxes = {}, {}
-        for c in scores.keys():
-            d_scores[c], d_bboxes[c] = bboxes_sort(scores[c], bboxes[c], top_k=top_k)
-        return d_scores, d_bboxes
+        # all classes in one launch: the kernel takes [S, N] rows, S = classes x images
+        keys = list(scores.keys())
+        s, b = core.stack_classes(scores, keys), core.stack_classes(bboxes, keys)
+        C, B = int(s.shape[0]), int(s.shape[1])
+        os_, ob, _ = core.sort_topk(s.reshape(C * B, -1), b.reshape(C * B, -1, 4), top_k)
+        os_, ob = os_.view(C, B, -1), ob.view(C, B, -1, 4)
+        return {c: os_[i] for i, c in enumerate(keys)}, {c: ob[i] for i, c in enumerate(keys)}
     s, b, _ = core.sort_topk(scores, bboxes, top_k)
     return s, b
 
@@ -36,7 +39,12 @@ def bboxes_sort(scores, bboxes, top_k=400, scope=None):
 def bboxes_clip(bbox_ref, bboxes, scope=None):
     """reference :105-144."""
     if isinstance(bboxes, dict):
-        return {c: bboxes_clip(bbox_ref, bboxes[c]) for c in bboxes.keys()}
+        keys = list(bboxes.keys())
+        shapes = {tuple(bboxes[c].shape) for c in keys}
+        if len(shapes) == 1:                                   # one launch over all classes
+            out = core.clip(bbox_ref, core.stack_classes(bboxes, keys))
+            return {c: out[i] for i, c in enumerate(keys)}
+        return {c: bboxes_clip(bbox_ref, bboxes[c]) for c in keys}
     return core.clip(bbox_ref, bboxes)
 
 
@@ -60,11 +68,13 @@ def bboxes_nms(scores, bboxes, nms_threshold=0.5, keep_top_k=200, mode='min', sc
 def bboxes_nms_batch(scores, bboxes, nms_threshold=0.5, keep_top_k=200, scope=None, mode='min'):
     """reference :262-302 (always mode 'min' there; ``mode`` is an addition)."""
     if isinstance(scores, dict) or isinstance(bboxes, dict):
-        d_scores, d_bboxes = {}, {}
-        for c in scores.keys():
-            d_scores[c], d_bboxes[c] = bboxes_nms_batch(scores[c], bboxes[c], nms_threshold=nms_threshold,
-                                                        keep_top_k=keep_top_k, mode=mode)
-        return d_scores, d_bboxes
+        # all classes in one launch (two with the re-sort): rows = classes x images
+        keys = list(scores.keys())
+        s, b = core.stack_classes(scores, keys), core.stack_classes(bboxes, keys)
+        C, B = int(s.shape[0]), int(s.shape[1])
+        os_, ob, _ = core.nms_batch(s.reshape(C * B, -1), b.reshape(C * B, -1, 4), nms_threshold, keep_top_k, mode)
+        os_, ob = os_.view(C, B, -1), ob.view(C, B, -1, 4)
+        return {c: os_[i] for i, c in enumerate(keys)}, {c: ob[i] for i, c in enumerate(keys)}
     os_, ob, _ = core.nms_batch(scores, bboxes, nms_threshold, keep_top_k, mode)
     return os_, ob
 

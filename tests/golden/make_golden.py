@@ -502,7 +502,46 @@ def gen_tfrecord():
     print('%-30s %8.1f KB' % ('voc_synth_000.tfrecord', os.path.getsize(os.path.join(HERE, 'voc_synth_000.tfrecord')) / 1024.))
 
 
+# --------------------------------------------------------------------------- #
+# stand-alone pieces the fused path folds into kernels: RONNet.bboxes_filter_min (tensor and dict form),
+# tfe.tensors.pad_axis, tfe.math.safe_divide
+# --------------------------------------------------------------------------- #
+def gen_filter_min():
+    from tf_extended import tensors as tfe_tensors, math as tfe_math
+    rng = np.random.Generator(np.random.PCG64(808))
+    net = ron_vgg_320.RONNet()
+    N = 300
+    out = {}
+    c = rng.uniform(0.1, 0.9, size=(3, N, 2))
+    sz = rng.uniform(0.0, 0.09, size=(3, N, 2))               # about half of the boxes are below 0.03 in one side
+    boxes = np.concatenate([c - sz / 2, c + sz / 2], -1).astype(np.float32)
+    boxes[0, 7] = [0.2, 0.2, 0.23, 0.5]                        # width ok, height exactly 0.03 (float32): strict >
+    boxes[1, :40] = 0                                          # zeroed (masked) entries never survive
+    scores = rng.uniform(0, 1, size=(3, N)).astype(np.float32)
+    out['in_scores'], out['in_boxes'] = scores, boxes
+    for top_k in (50, 400):
+        s, b = net.bboxes_filter_min(T(scores[0:1]), T(boxes[0:1]), top_k)
+        out['k%d_scores' % top_k], out['k%d_boxes' % top_k] = npy(s), npy(b)
+        ds, db = net.bboxes_filter_min({c + 1: T(scores[c:c + 1]) for c in range(3)}, {c + 1: T(boxes[c:c + 1]) for c in range(3)},
+                                       top_k, minsize=0.04)
+        for c in (1, 2, 3):
+            out['k%d_dict_scores_%d' % (top_k, c)], out['k%d_dict_boxes_%d' % (top_k, c)] = npy(ds[c]), npy(db[c])
+    x = rng.normal(size=(4, 5, 3)).astype(np.float32)
+    out['pad_in'] = x
+    for axis, size in ((0, 9), (1, 5), (1, 3), (2, 7)):
+        out['pad_axis%d_size%d' % (axis, size)] = npy(tfe_tensors.pad_axis(T(x), 0, size, axis=axis))
+    num = rng.normal(size=64).astype(np.float32)
+    den = rng.normal(size=64).astype(np.float32)
+    den[::7] = 0.
+    out['div_num'], out['div_den'] = num, den
+    out['div_out'] = npy(tfe_math.safe_divide(T(num), T(den), 'x'))
+    save('filter_min', **out)
+
+
 if __name__ == '__main__':
+    if '--only-filter-min' in sys.argv:
+        gen_filter_min()
+        sys.exit(0)
     if '--only-tfrecord' in sys.argv:
         gen_tfrecord()
         sys.exit(0)
@@ -531,3 +570,4 @@ if __name__ == '__main__':
     gen_np_methods()
     gen_voc_eval()
     gen_tfrecord()
+    gen_filter_min()

@@ -211,3 +211,60 @@ def test_encode_extreme_coordinates(ron, batch):
         eq(r['labels'][b], o['labels'], 'labels[%d]' % b)
         eq(r['scores'][b], o['scores'], 'scores[%d]' % b)
         eq(r['loc'][b], o['loc'], 'loc[%d]' % b)
+
+
+def test_caller_supplied_anchors_are_used_as_given(ron):
+    """The reference always computes with the anchors it is handed.  A plain list of (y, x, h, w) arrays, a copied list,
+    or a list whose arrays were edited after RONNet.anchors returned it must not be replaced by the cached default set."""
+    import torch
+    net, anchors = ron
+    spec = O.RON320
+    moved = []
+    for (y, x, h, w) in anchors:
+        moved.append((y + np.float32(0.013), x - np.float32(0.007), (h * np.float32(1.1)).astype(np.float32), w))
+    enc, cor, inside = O.encode_anchor_tables(moved, spec.img_shape, spec.allowed_borders)
+    boxes, labels, counts = synth.make_gt_batch(2, 1, 9, 9)
+    want = O.encode_image(labels[0, :9], boxes[0, :9], enc, cor, inside, 0.5, 0.3)
+    edited = type(anchors)(moved)                       # an AnchorList that still carries the default handle ...
+    edited.anchor_set, edited.fingerprint = anchors.anchor_set, anchors.fingerprint   # ... and its stale fingerprint
+    for what, a in (('plain list', list(moved)), ('edited AnchorList', edited)):
+        lab, loc, sco, box = net.bboxes_encode(labels[0, :9], boxes[0, :9], a, positive_threshold=0.5, ignore_threshold=0.3)
+        eq(torch.cat([t.reshape(-1) for t in lab]), want['labels'], what + ': labels')
+        eq(torch.cat([t.reshape(-1) for t in sco]), want['scores'], what + ': scores')
+        eq(torch.cat([t.reshape(-1, 4) for t in loc]), want['loc'], what + ': loc')
+        eq(torch.cat([t.reshape(-1, 4) for t in box]), cor, what + ': anchor corner boxes')
+    r = net.bboxes_encode_batch(labels, boxes, counts, list(moved), 0.5, 0.3)
+    eq(r['labels'][0], want['labels'], 'batched form with a plain list')
+    # decode with the moved anchors
+    loc_in = np.random.Generator(np.random.PCG64(3)).normal(0, 0.3, size=(1, 21250, 4)).astype(np.float32)
+    ls = anchors.anchor_set.layers
+    per_layer = [loc_in[:, o:o + H * W * A].reshape(1, H, W, A, 4) for (H, W, A, o) in ls]
+    got = net.bboxes_decode(per_layer, list(moved))
+    eq(torch.cat([t.reshape(1, -1, 4) for t in got], 1)[0], O.decode(loc_in[0], O.flat_decode_anchors(moved)), 'decode')
+    # the untouched list still takes the fast path (its own handle)
+    assert net._resolve(anchors) is anchors.anchor_set and net._resolve(list(anchors)) is None
+
+
+def test_two_graph_captures_do_not_share_a_workspace(ron):
+    """Two CUDA-graph captures of the same encode shape, replayed in the opposite order: each capture owns a workspace
+    that its own graph zeroes (a cached buffer allocated inside the first capture would be zeroed by graph 1 only)."""
+    import torch
+    from ron_tensorflow_b200 import core
+    net, anchors = ron
+    aset = anchors.anchor_set
+    ba, la, ca = synth.make_gt_batch(2, 4, 1, 30, g_max=30)
+    bb, lb, cb = synth.make_gt_batch(2, 4, 1, 30, g_max=30, first_image=50)
+    da = [torch.from_numpy(x).cuda() for x in (ba, la, ca)]
+    db = [torch.from_numpy(x).cuda() for x in (bb, lb, cb)]
+    fn = lambda b, l, c: core.match_encode(aset, b, l, c, 0.5, 0.3, want_matched=True)
+    core._ws_cache.clear()
+    g1 = core.Graphed(fn, *da)
+    g2 = core.Graphed(fn, *db)
+    r2 = {k: v.clone() for k, v in g2.replay().items()}
+    r1 = {k: v.clone() for k, v in g1.replay().items()}
+    r2b = g2.replay()
+    w1, w2 = fn(*da), fn(*db)
+    for k in ('labels', 'loc', 'scores', 'matched'):
+        eq(r1[k], w1[k], 'graph 1 ' + k)
+        eq(r2[k], w2[k], 'graph 2 (replayed first) ' + k)
+        eq(r2b[k], w2[k], 'graph 2 again ' + k)

@@ -416,3 +416,81 @@ def test_device_tpfp_state_matches_host_accumulation():
     small.update(*d)
     with pytest.raises(RuntimeError):
         small.to_host()
+
+
+def test_filter_min_pad_axis_safe_divide(golden):
+    """RONNet.bboxes_filter_min stand-alone (tensor and dict forms, nets/ron_vgg_320.py:196-233), tfe.pad_axis and
+    tfe.safe_divide against vectors recorded from the reference's own functions; then the batched form (every image of a
+    batch, all classes in two launches) against the oracle image by image."""
+    need_cuda()
+    import torch
+    import ron_tensorflow_b200.tf_extended as tfe
+    from ron_tensorflow_b200.nets import ron_vgg_320
+    net = ron_vgg_320.RONNet()
+    g = golden('filter_min')
+    for top_k in (50, 400):
+        s, b = net.bboxes_filter_min(g['in_scores'][0:1], g['in_boxes'][0:1], top_k)
+        eq(s, g['k%d_scores' % top_k], 'scores top_k=%d' % top_k)
+        eq(b, g['k%d_boxes' % top_k], 'boxes')
+        ds, db = net.bboxes_filter_min({c: g['in_scores'][c - 1:c] for c in (1, 2, 3)}, {c: g['in_boxes'][c - 1:c] for c in (1, 2, 3)},
+                                       top_k, minsize=0.04)
+        for c in (1, 2, 3):
+            eq(ds[c], g['k%d_dict_scores_%d' % (top_k, c)], 'dict scores class %d top_k=%d' % (c, top_k))
+            eq(db[c], g['k%d_dict_boxes_%d' % (top_k, c)], 'dict boxes')
+    x = torch.from_numpy(g['pad_in']).cuda()
+    for axis, size in ((0, 9), (1, 5), (1, 3), (2, 7)):
+        eq(tfe.pad_axis(x, 0, size, axis=axis), g['pad_axis%d_size%d' % (axis, size)], 'pad_axis')
+    eq(tfe.safe_divide(torch.from_numpy(g['div_num']).cuda(), torch.from_numpy(g['div_den']).cuda()), g['div_out'], 'safe_divide')
+    # batched: B images x 4 classes, the reference semantics image by image (it only accepts batch 1, :221)
+    rng = np.random.Generator(np.random.PCG64(4))
+    B, N, K = 5, 700, 120
+    c = rng.uniform(0.1, 0.9, size=(4, B, N, 2))
+    sz = rng.uniform(0., 0.08, size=(4, B, N, 2))
+    boxes = np.concatenate([c - sz / 2, c + sz / 2], -1).astype(np.float32)
+    scores = rng.uniform(0, 1, size=(4, B, N)).astype(np.float32)
+    ds, db = net.bboxes_filter_min({k + 1: scores[k] for k in range(4)}, {k + 1: boxes[k] for k in range(4)}, K)
+    for k in range(4):
+        rows = [O.bboxes_filter_min(scores[k, i], boxes[k, i], K) for i in range(B)]
+        width = max(r[0].shape[0] for r in rows)
+        assert tuple(ds[k + 1].shape) == (B, width)
+        for i, (s_, b_) in enumerate(rows):
+            eq(ds[k + 1][i, :s_.shape[0]], s_, 'class %d image %d' % (k + 1, i))
+            eq(db[k + 1][i, :s_.shape[0]], b_, 'boxes')
+            assert float(ds[k + 1][i, s_.shape[0]:].abs().sum()) == 0.
+
+
+def test_ssd512_batch128_sampled():
+    """BASELINE configs[3] at its stated batch size: SSD-512 anchor set, batch 128 -- post-process (SSD order) and
+    match+encode, bit-exact against the oracle on a sample of the images."""
+    need_cuda()
+    from ron_tensorflow_b200.nets import ssd_vgg_512
+    net = ssd_vgg_512.SSDNet()
+    anchors = net.anchors(net.params.img_shape)
+    ls = anchors.anchor_set.layer_sizes
+    B = 128
+    loc, pred, _ = synth.make_predictions(4000, B, 24564, 21, hot=300)
+    oanch = O.anchors_all_layers(O.SSD512)
+    dec = O.flat_decode_anchors(oanch)
+    ns, nb = net.detect(synth.split_layers(pred, ls), synth.split_layers(loc, ls), select_threshold=0.01,
+                        nms_threshold=0.45, top_k=400, keep_top_k=200)
+    for b in (0, 63, 127):
+        o = O.detected_bboxes_image(pred[b], loc[b], dec, None, None, 0.01, 0.45, None, 400, 200, min_size=None)
+        eq(ns[b], o['scores'], 'scores b=%d' % b)
+        eq(nb[b], o['boxes'], 'boxes b=%d' % b)
+    del ns, nb
+    boxes, labels, counts = synth.make_gt_batch(4, B, 1, 50)
+    enc, cor, inside = O.encode_anchor_tables(oanch, O.SSD512.img_shape, None)
+    import os
+    for kernel in ('grid', 'generic'):
+        os.environ['RONK_ENC_KERNEL'] = kernel
+        try:
+            r = net.bboxes_encode_batch(labels, boxes, counts, anchors, 0.5, 0.5, want_matched=True, want_objness=True)
+        finally:
+            del os.environ['RONK_ENC_KERNEL']
+        for b in (0, 31, 77, 127):
+            o = O.encode_image(labels[b, :counts[b]], boxes[b, :counts[b]], enc, cor, inside, 0.5, 0.5)
+            eq(r['matched'][b], o['matched'].astype(np.int32), '%s matched[%d]' % (kernel, b))
+            eq(r['labels'][b], o['labels'], 'labels')
+            eq(r['scores'][b], o['scores'], 'scores')
+            eq(r['loc'][b], o['loc'], 'loc')
+            eq(r['objness'][b], o['objness'], 'objness')

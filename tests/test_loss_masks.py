@@ -140,3 +140,52 @@ def test_cuda_loss_masks_batch64_and_edge_cases():
     sel = d['final_neg_mask_objness'].to('cpu').numpy()
     assert sel[pos].all() and not sel[gcls < 0].any()
     assert abs(sel[gcls == 0].sum() - 3 * pos.sum()) < 0.02 * 3 * pos.sum()
+
+
+@pytest.mark.gpu
+def test_localization_loss_and_smooth_l1_are_differentiable():
+    """In the reference the localisation term is a training loss differentiated w.r.t. the network's localisations
+    (glocalisations sits under tf.stop_gradient, nets/ron_vgg_320.py:760): loss.backward() must reach them, with the
+    gradient of a plain float32 torch restatement of the same formula; modified_smooth_l1 likewise, element-wise."""
+    need_cuda()
+    import torch
+    from ron_tensorflow_b200.nets import ron_vgg_320 as rv, custom_layers
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    n = 5000
+    loc = (torch.randn((n, 4), device='cuda', generator=gen) * 0.4).requires_grad_()
+    gloc = torch.randn((n, 4), device='cuda', generator=gen) * 0.4
+    mask = torch.rand((n,), device='cuda', generator=gen) < 0.2
+
+    def torch_smooth(x, sigma):
+        s2 = sigma * sigma
+        return torch.where(x.abs() < 1. / s2, 0.5 * s2 * x * x, x.abs() - 0.5 / s2)
+
+    loss = rv.ron_localization_loss(loc, gloc, mask)
+    (3. * loss).backward()
+    ref_in = loc.detach().clone().requires_grad_()
+    ref = (1. / 3) * torch_smooth(ref_in - gloc, 3.)[mask].sum(-1).mean()
+    (3. * ref).backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    assert torch.allclose(loc.grad, ref_in.grad, rtol=1e-5, atol=1e-9)
+    assert float(loc.grad[~mask].abs().sum()) == 0.
+    # through ron_loss_masks (the fused launch yields the value; with grad-requiring localisations the differentiable form)
+    labels = torch.randint(-1, 5, (n,), device='cuda', generator=gen)
+    obj = torch.rand((n,), device='cuda', generator=gen)
+    loc2 = loc.detach().clone().requires_grad_()
+    out = rv.ron_loss_masks(labels, obj, torch.rand((n,), device='cuda', generator=gen), torch.rand((n,), device='cuda', generator=gen),
+                            localisations=loc2, glocalisations=gloc)
+    assert out['localization_loss'].requires_grad
+    out['localization_loss'].backward()
+    m2 = out['cls_positive_mask']
+    ref2_in = loc.detach().clone().requires_grad_()
+    if int(m2.sum()):
+        ((1. / 3) * torch_smooth(ref2_in - gloc, 3.)[m2].sum(-1).mean()).backward()
+        assert torch.allclose(loc2.grad, ref2_in.grad, rtol=1e-5, atol=1e-9)
+    # element-wise smooth L1, gradient to both arguments
+    a = (torch.randn((300, 4), device='cuda', generator=gen)).requires_grad_()
+    b = (torch.randn((300, 4), device='cuda', generator=gen)).requires_grad_()
+    w = torch.rand((300, 4), device='cuda', generator=gen)
+    (custom_layers.modified_smooth_l1(a, b, 1., 1., sigma=2.) * w).sum().backward()
+    a2, b2 = a.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    (torch_smooth(a2 - b2, 2.) * w).sum().backward()
+    assert torch.allclose(a.grad, a2.grad, rtol=1e-5, atol=1e-9) and torch.allclose(b.grad, b2.grad, rtol=1e-5, atol=1e-9)
