@@ -171,6 +171,22 @@ int ronk_nms_batch(const float* scores, const float* boxes, int S, int K,
                    float nms_threshold, int keep_top_k, int mode, int assume_sorted,
                    float* out_scores, float* out_boxes, int32_t* out_idx,
                    void* ws, void* stream);
+/* Two-tier top-k for large K (the fused detect path): greedy NMS walks the sorted candidates and stops after keep_top_k
+ * picks, so it rarely looks past the first few hundred.  Tier 1 = ronk_decode_select_topk with K1 = min(K, 1024) +
+ * ronk_nms_batch_tiered(out_short): a row is marked when its K1 candidates ran out before keep_top_k boxes were kept.
+ * Tier 2, for the marked rows only (the others return at once and keep their tier-1 outputs): ronk_select_topk_flagged
+ * re-selects with the full K from the same workspace (an exact rebuild of the candidate list where the tier-1 pivot
+ * cut it short) and ronk_nms_batch_tiered(only_flagged) redoes their NMS.  Results are those of one tier with K. */
+int ronk_select_topk_flagged(const ronk_anchors_t* h,
+                             const float* const* loc_layers_host, const float* const* cls_layers_host,
+                             const float* const* obj_layers_host,
+                             int B, int C, float objectness_threshold, float select_threshold,
+                             const float* clip_host, float min_size, const float* prior_scaling_host, int K,
+                             int select_flags, const int32_t* flags,
+                             float* out_scores, float* out_boxes, int32_t* out_idx, void* ws, void* stream);
+int ronk_nms_batch_tiered(const float* scores, const float* boxes, int S, int K, float nms_threshold,
+                          int keep_top_k, int mode, const int32_t* only_flagged, int32_t* out_short,
+                          float* out_scores, float* out_boxes, int32_t* out_idx, void* stream);
 
 /* ---------------------------------------------------------------------- TP/FP
  * Replaces tfe.bboxes_matching_batch -> bboxes_matching -> bboxes_jaccard

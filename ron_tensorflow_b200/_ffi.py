@@ -41,6 +41,11 @@ SIGNATURES = {
     'ronk_decode_select_topk': (c_int, [c_void_p, P(c_void_p), P(c_void_p), P(c_void_p), c_int, c_int, c_float,
                                         c_float, P(c_float), c_float, P(c_float), c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ronk_select_topk_flagged': (c_int, [c_void_p, P(c_void_p), P(c_void_p), P(c_void_p), c_int, c_int, c_float,
+                                         c_float, P(c_float), c_float, P(c_float), c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ronk_nms_batch_tiered': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     'ronk_sort_topk': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ronk_clip': (c_int, [P(c_float), c_void_p, c_longlong, c_void_p, c_void_p]),
     'ronk_nms_workspace_bytes': (c_size_t, [c_int, c_int]),

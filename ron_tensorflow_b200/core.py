@@ -12,6 +12,7 @@ import torch
 from . import _ffi
 
 _PS = (0.1, 0.1, 0.2, 0.2)
+SELECT_LOC_DECODED_FLAG = _ffi.SELECT_LOC_DECODED
 
 
 def _require_cuda():
@@ -348,6 +349,82 @@ def decode_select_topk(anchors, loc_layers, cls_layers, obj_layers=None, objectn
     _ffi.check(rc)
     del loc_t, cls_t, obj_t
     return scores, boxes, idx
+
+
+# select_nms: top_k beyond TIER_K takes the two-tier path.  Off by default (no top_k exceeds it): on the crowded-scene
+# workload of BASELINE configs[4] (dense 81-class scores, min-area overlap) NMS suppresses so much that nearly every row
+# walks past the first 1024 candidates, and the first tier is pure overhead there (7.2 ms instead of 4.3 ms per batch of
+# 16 at top_k = 10 000).  Set core.TIER_K = 1024 for detectors whose NMS stops early.
+TIER_K = 1 << 30
+
+
+def select_nms(anchors, loc_layers, cls_layers, obj_layers=None, objectness_threshold=0.0, select_threshold=None, clip=None,
+               min_size=None, top_k=400, keep_top_k=200, nms_threshold=0.5, mode='min', prior_scaling=_PS, loc_is_decoded=False,
+               want_idx=False):
+    """Fused post-process: decode + objectness gate + select + clip + min-size + per-class top-k, then NMS.
+    Returns scores [B,C-1,M], boxes [B,C-1,M,4] and, with want_idx, the anchor index of every kept box (int32, -1 =
+    padding).  top_k > TIER_K runs in two tiers (include/ronk.h, ronk_select_topk_flagged): greedy NMS stops after
+    keep_top_k picks, so the first TIER_K candidates nearly always suffice; the (image, class) rows that run out of
+    candidates before keep_top_k boxes are kept are redone with the full top_k.  Same results, and the cost of the
+    sort no longer grows with top_k."""
+    if mode not in ('min', 'union'):
+        raise ValueError('unknown mode to use for nms.')
+    dev = anchors.device
+    loc_t, loc_p, B = _layer_ptrs(anchors, loc_layers, 4, 'localisations')
+    C = int(as_cuda(cls_layers[0], torch.float32, dev).shape[-1])
+    cls_t, cls_p, B2 = _layer_ptrs(anchors, cls_layers, C, 'predictions')
+    if B2 != B:
+        raise ValueError('predictions and localisations disagree on the batch size')
+    obj_t, obj_p = None, None
+    if obj_layers is not None:
+        obj_t, obj_p, B3 = _layer_ptrs(anchors, obj_layers, 1, 'objectness')
+        if B3 != B:
+            raise ValueError('objectness and predictions disagree on the batch size')
+    K, M, CM = int(top_k), int(keep_top_k), C - 1
+    S = B * CM
+    K1 = min(K, TIER_K)
+    sel = 0.0 if select_threshold is None else float(select_threshold)
+    flags = SELECT_LOC_DECODED_FLAG if loc_is_decoded else 0
+    L = _ffi.lib()
+    ws = _workspace('sel', max(L.ronk_select_workspace_bytes(anchors.handle, B, C, K), 256), False, dev)
+    clip_a = _ffi.farr(clip) if clip is not None else None
+    ms = -1.0 if min_size is None else float(min_size)
+    ps = _ffi.farr(prior_scaling)
+    nmode = _ffi.NMS_MIN if mode == 'min' else _ffi.NMS_UNION
+
+    def topk_buffers(k):
+        return (torch.empty((S, k), dtype=torch.float32, device=dev), torch.empty((S, k, 4), dtype=torch.float32, device=dev),
+                torch.empty((S, k), dtype=torch.int32, device=dev) if want_idx else None)
+
+    s1, b1, i1 = topk_buffers(K1)
+    ns = torch.empty((S, M), dtype=torch.float32, device=dev)
+    nb = torch.empty((S, M, 4), dtype=torch.float32, device=dev)
+    ni = torch.empty((S, M), dtype=torch.int32, device=dev) if want_idx else None
+    short = torch.empty((S,), dtype=torch.int32, device=dev) if K > K1 else None
+    with torch.cuda.device(dev):
+        _ffi.check(L.ronk_decode_select_topk(anchors.handle, loc_p, cls_p, obj_p, B, C, float(objectness_threshold), sel, clip_a, ms,
+                                             ps, K1, flags, _ptr(s1), _ptr(b1), _ptr(i1), _ptr(ws), _stream()))
+        _ffi.check(L.ronk_nms_batch_tiered(_ptr(s1), _ptr(b1), S, K1, float(nms_threshold), M, nmode, None, _ptr(short),
+                                           _ptr(ns), _ptr(nb), _ptr(ni), _stream()))
+    aidx = None
+    if want_idx:
+        nl = ni.long()
+        aidx = torch.where(nl >= 0, torch.gather(i1.long(), 1, nl.clamp(min=0)), nl)
+    if K > K1:
+        s2, b2, i2 = topk_buffers(K)
+        ni2 = torch.empty((S, M), dtype=torch.int32, device=dev) if want_idx else None
+        with torch.cuda.device(dev):
+            _ffi.check(L.ronk_select_topk_flagged(anchors.handle, loc_p, cls_p, obj_p, B, C, float(objectness_threshold), sel, clip_a,
+                                                  ms, ps, K, flags, _ptr(short), _ptr(s2), _ptr(b2), _ptr(i2), _ptr(ws), _stream()))
+            _ffi.check(L.ronk_nms_batch_tiered(_ptr(s2), _ptr(b2), S, K, float(nms_threshold), M, nmode, _ptr(short), None,
+                                               _ptr(ns), _ptr(nb), _ptr(ni2), _stream()))
+        if want_idx:
+            nl2 = ni2.long()
+            redo = (short != 0).unsqueeze(1)
+            a2 = torch.where(nl2 >= 0, torch.gather(i2.long(), 1, nl2.clamp(min=0)), nl2)
+            aidx = torch.where(redo, a2, aidx)
+    del loc_t, cls_t, obj_t
+    return ns.view(B, CM, M), nb.view(B, CM, M, 4), (aidx.view(B, CM, M).int() if want_idx else None)
 
 
 def sort_topk(scores, boxes, top_k, want_idx=False):

@@ -33,6 +33,8 @@ struct NmsParams {
     float* out_scores;
     float4* out_boxes;
     int* out_idx;
+    const int* only_flagged;   // [S] or NULL: segments whose flag is 0 are left alone
+    int* out_short;            // [S] or NULL: 1 when all K candidates were walked and fewer than M were kept
 };
 
 // does kept box i suppress candidate j?  (j is the later one: tf_extended/bboxes.py:195-211)
@@ -63,6 +65,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.x * kNmsWarps + warp;
     if (seg >= p.S) return;
+    if (p.only_flagged && !p.only_flagged[seg]) return;
     // per warp: float4 + float for M kept (+ kNmsPad sentinels) and 32 chunk entries, + thr * vol
     const int per_warp = nms_smem_per_warp(p.M);
     unsigned char* base = smem + (size_t)warp * per_warp;
@@ -177,6 +180,7 @@ nms_kernel(const __grid_constant__ NmsParams p) {
         count += __popc(kept);
         __syncwarp();
     }
+    if (p.out_short && lane == 0) p.out_short[seg] = count < p.M ? 1 : 0;
     for (int r = count + lane; r < p.M; r += 32) {   // pad_axis (tensors.py:59-86)
         p.out_scores[out0 + r] = 0.f;
         p.out_boxes[out0 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -216,9 +220,30 @@ extern "C" size_t ronk_nms_workspace_bytes(int S, int K) {
     return (size_t)S * K * sizeof(int);
 }
 
+static int nms_launch(const float* scores, const float* boxes, int S, int K, float nms_threshold, int keep_top_k, int mode,
+                      int assume_sorted, const int32_t* only_flagged, int32_t* out_short, float* out_scores,
+                      float* out_boxes, int32_t* out_idx, void* ws, void* stream);
+
 extern "C" int ronk_nms_batch(const float* scores, const float* boxes, int S, int K, float nms_threshold,
                               int keep_top_k, int mode, int assume_sorted, float* out_scores, float* out_boxes,
                               int32_t* out_idx, void* ws, void* stream) {
+    return nms_launch(scores, boxes, S, K, nms_threshold, keep_top_k, mode, assume_sorted, nullptr, nullptr, out_scores,
+                      out_boxes, out_idx, ws, stream);
+}
+
+// Sorted rows only.  only_flagged (or NULL): rows whose flag is 0 are skipped, their outputs stay as they are.
+// out_short (or NULL): 1 for a row whose K candidates were all walked with fewer than keep_top_k kept -- with more
+// candidates than K available the greedy loop of the reference would have gone on (two-tier top-k, see ronk.h).
+extern "C" int ronk_nms_batch_tiered(const float* scores, const float* boxes, int S, int K, float nms_threshold,
+                                     int keep_top_k, int mode, const int32_t* only_flagged, int32_t* out_short,
+                                     float* out_scores, float* out_boxes, int32_t* out_idx, void* stream) {
+    return nms_launch(scores, boxes, S, K, nms_threshold, keep_top_k, mode, 1, only_flagged, out_short, out_scores, out_boxes,
+                      out_idx, nullptr, stream);
+}
+
+static int nms_launch(const float* scores, const float* boxes, int S, int K, float nms_threshold, int keep_top_k, int mode,
+                      int assume_sorted, const int32_t* only_flagged, int32_t* out_short, float* out_scores,
+                      float* out_boxes, int32_t* out_idx, void* ws, void* stream) {
     RONK_REQUIRE(scores && boxes && out_scores && out_boxes, RONK_EINVAL, "ronk_nms_batch: NULL argument");
     RONK_REQUIRE(S >= 1 && K >= 1 && keep_top_k >= 1, RONK_EINVAL, "ronk_nms_batch: S, K, keep_top_k must be >= 1");
     RONK_REQUIRE(mode == RONK_NMS_MIN || mode == RONK_NMS_UNION, RONK_EINVAL, "unknown mode to use for nms.");
@@ -236,6 +261,8 @@ extern "C" int ronk_nms_batch(const float* scores, const float* boxes, int S, in
     p.out_scores = out_scores;
     p.out_boxes = (float4*)out_boxes;
     p.out_idx = out_idx;
+    p.only_flagged = only_flagged;
+    p.out_short = out_short;
     if (!assume_sorted) {
         int P = 1;
         while (P < K) P <<= 1;

@@ -47,6 +47,7 @@ struct PostParams {
     float* out_scores;
     float4* out_boxes;
     int* out_idx;
+    const int* only_flagged;         // select_topk_kernel: when given, segments whose flag is 0 are left alone
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -641,6 +642,7 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
     __shared__ int s_cnt;
     const int tid = threadIdx.x;
     const int seg = blockIdx.x;
+    if (p.only_flagged && !p.only_flagged[seg]) return;          // second tier: only the segments that asked for more
     const int CM = p.C - 1;
     const int b = seg / CM;
     int n = p.counts[seg];
@@ -820,12 +822,13 @@ extern "C" size_t ronk_select_workspace_bytes(const ronk_anchors_t* h, int B, in
     return 2 * align_up(segs * sizeof(int), 256) + segs * (size_t)h->tab.N * sizeof(u64) + (size_t)B * h->tab.N * 16;
 }
 
-extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* const* loc_layers,
-                                       const float* const* cls_layers, const float* const* obj_layers, int B,
-                                       int C, float objectness_threshold, float select_threshold,
-                                       const float* clip, float min_size, const float* ps, int K,
-                                       int select_flags, float* out_scores, float* out_boxes, int32_t* out_idx, void* ws,
-                                       void* stream) {
+// argument checks + everything of PostParams that does not depend on which launches follow
+static int fill_post_params(PostParams& p, const char* who, const ronk_anchors_t* h, const float* const* loc_layers,
+                            const float* const* cls_layers, const float* const* obj_layers, int B, int C,
+                            float objectness_threshold, float select_threshold, const float* clip, float min_size,
+                            const float* ps, int K, int select_flags, float* out_scores, float* out_boxes, int32_t* out_idx,
+                            void* ws) {
+    (void)who;
     RONK_REQUIRE(h != nullptr, RONK_EINVAL, "ronk_decode_select_topk: NULL anchor handle");
     RONK_REQUIRE(loc_layers && cls_layers && ps && out_scores && out_boxes && ws, RONK_EINVAL,
                  "ronk_decode_select_topk: NULL pointer argument");
@@ -835,7 +838,6 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
                  "ronk_decode_select_topk: select_threshold must be >= 0 (None in the reference is 0)");
     RONK_REQUIRE(((uintptr_t)out_boxes % 16) == 0 && ((uintptr_t)ws % 256) == 0, RONK_EINVAL,
                  "ronk_decode_select_topk: out_boxes must be 16-byte and ws 256-byte aligned");
-    PostParams p;
     p.tab = h->tab;
     int toff = 0;
     for (int l = 0; l < h->tab.L; ++l) {
@@ -874,6 +876,53 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     p.out_scores = out_scores;
     p.out_boxes = (float4*)out_boxes;
     p.out_idx = out_idx;
+    p.only_flagged = nullptr;
+    p.force_rebuild = (select_flags & RONK_SELECT_TEST_REBUILD) ? 1 : 0;
+    p.pivot_rank = 0;
+    p.tile_tab = (const int4*)h->d_tile_tab;
+    p.r_lo = p.r_hi = 0;
+    return RONK_OK;
+}
+
+static int launch_select_topk(const PostParams& p, size_t segs, cudaStream_t st) {
+    int P = 1;
+    while (P < p.K) P <<= 1;
+    size_t smem_b = (size_t)(P + kListCap) * sizeof(u64) + (size_t)kBins * sizeof(unsigned);
+    if (smem_b > 48 * 1024)
+        RONK_CUDA(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    select_topk_kernel<<<(unsigned)segs, kTopkThreads, smem_b, st>>>(p);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+// Second tier of a two-tier top-k (see ronk.h): the key lists / box table of an earlier ronk_decode_select_topk call
+// on the same inputs and workspace are selected again with a larger K, for the segments whose flag is set only.
+extern "C" int ronk_select_topk_flagged(const ronk_anchors_t* h, const float* const* loc_layers,
+                                        const float* const* cls_layers, const float* const* obj_layers, int B, int C,
+                                        float objectness_threshold, float select_threshold, const float* clip,
+                                        float min_size, const float* ps, int K, int select_flags, const int32_t* flags,
+                                        float* out_scores, float* out_boxes, int32_t* out_idx, void* ws, void* stream) {
+    RONK_REQUIRE(flags != nullptr, RONK_EINVAL, "ronk_select_topk_flagged: NULL flags");
+    PostParams p;
+    if (int rc = fill_post_params(p, "ronk_select_topk_flagged", h, loc_layers, cls_layers, obj_layers, B, C, objectness_threshold,
+                                  select_threshold, clip, min_size, ps, K, select_flags, out_scores, out_boxes, out_idx, ws))
+        return rc;
+    p.only_flagged = flags;
+    return launch_select_topk(p, (size_t)B * (C - 1), (cudaStream_t)stream);
+}
+
+extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* const* loc_layers,
+                                       const float* const* cls_layers, const float* const* obj_layers, int B,
+                                       int C, float objectness_threshold, float select_threshold,
+                                       const float* clip, float min_size, const float* ps, int K,
+                                       int select_flags, float* out_scores, float* out_boxes, int32_t* out_idx, void* ws,
+                                       void* stream) {
+    PostParams p;
+    if (int rc = fill_post_params(p, "ronk_decode_select_topk", h, loc_layers, cls_layers, obj_layers, B, C, objectness_threshold,
+                                  select_threshold, clip, min_size, ps, K, select_flags, out_scores, out_boxes, out_idx, ws))
+        return rc;
+    const size_t segs = (size_t)B * (C - 1);
+    const int toff = p.tile_off[h->tab.L];
     cudaStream_t st = (cudaStream_t)stream;
 
     init_segments_kernel<<<(unsigned)((segs + 255) / 256), 256, 0, st>>>(p.counts, p.thr, p.sel_thr, segs);
@@ -892,10 +941,7 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
     // then all other tiles with the pivot as threshold.  perm_mul ~ 0.618 * tiles, coprime.
     const int tpi = h->tiles_per_image;        // == toff; the handle's tile table is in the permuted order
     const int m = h->tile_perm_mul;
-    p.tile_tab = (const int4*)h->d_tile_tab;
     int tpi1 = 0;
-    p.pivot_rank = 0;
-    p.force_rebuild = (select_flags & RONK_SELECT_TEST_REBUILD) ? 1 : 0;
     if (!(select_flags & RONK_SELECT_NO_SAMPLING) && tpi >= 16 && (long long)K * 8 <= h->tab.N) {
         tpi1 = tpi / 16;                 // a sixteenth of the tiles: pivot rank mu + 4 sigma + 8 still leaves ~2K keys per list
         if (tpi1 < 2) tpi1 = 2;
@@ -932,14 +978,7 @@ extern "C" int ronk_decode_select_topk(const ronk_anchors_t* h, const float* con
         if (int rc = launch_scatter(0, tpi)) return rc;
     }
 
-    int P = 1;
-    while (P < K) P <<= 1;
-    size_t smem_b = (size_t)(P + kListCap) * sizeof(u64) + (size_t)kBins * sizeof(unsigned);
-    if (smem_b > 48 * 1024)
-        RONK_CUDA(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    select_topk_kernel<<<(unsigned)segs, kTopkThreads, smem_b, st>>>(p);
-    RONK_LAUNCHED();
-    return RONK_OK;
+    return launch_select_topk(p, segs, st);
 }
 
 extern "C" int ronk_decode(const ronk_anchors_t* h, const float* loc, int B, int first_anchor, int n,

@@ -184,19 +184,14 @@ class RONNet(object):
         scores (+ objectness) -> decode, objectness gate, select, clip, min-size, per-class top-k,
         NMS.  Returns scores [B,C-1,M], boxes [B,C-1,M,4] (and anchor indices when asked)."""
         a = self._resolve(None)
-        s, b, ix = core.decode_select_topk(a, feat_localizations, predictions, objness, objectness_threshold,
-                                           select_threshold, clipping_bbox, minsize, top_k,
-                                           self.params.prior_scaling, want_idx=want_idx)
-        B, CM, K = s.shape
-        ns, nb, ni = core.nms_batch(s.view(B * CM, K), b.view(B * CM, K, 4), nms_threshold, keep_top_k, mode,
-                                    assume_sorted=True, want_idx=want_idx)
-        ns, nb = ns.view(B, CM, -1), nb.view(B, CM, -1, 4)
+        ns, nb, aidx = core.select_nms(a, feat_localizations, predictions, objness, objectness_threshold, select_threshold,
+                                       clipping_bbox, minsize, top_k, keep_top_k, nms_threshold, mode,
+                                       self.params.prior_scaling, want_idx=want_idx)
         if as_dict:
+            CM = ns.shape[1]
             return {c + 1: ns[:, c] for c in range(CM)}, {c + 1: nb[:, c] for c in range(CM)}
         if want_idx:
-            ni = ni.view(B, CM, -1).long()
-            aidx = torch.where(ni >= 0, torch.gather(ix.long(), 2, ni.clamp(min=0)), ni)
-            return ns, nb, aidx.int()
+            return ns, nb, aidx
         return ns, nb
 
 

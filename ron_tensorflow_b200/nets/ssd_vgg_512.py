@@ -122,9 +122,6 @@ class SSDNet(object):
                keep_top_k=200, mode='min'):
         """Fused SSD post-process from raw localisations (decode inside the select kernel)."""
         a = self._resolve(None)
-        s, b, _ = core.decode_select_topk(a, feat_localizations, predictions, None, 0.0, select_threshold, None,
-                                          None, top_k, self.params.prior_scaling)
-        B, CM, K = s.shape
-        ns, nb, _ = core.nms_batch(s.view(B * CM, K), b.view(B * CM, K, 4), nms_threshold, keep_top_k, mode,
-                                   assume_sorted=True)
-        return ns.view(B, CM, -1), nb.view(B, CM, -1, 4)
+        ns, nb, _ = core.select_nms(a, feat_localizations, predictions, None, 0.0, select_threshold, None, None, top_k,
+                                    keep_top_k, nms_threshold, mode, self.params.prior_scaling)
+        return ns, nb

@@ -494,3 +494,29 @@ def test_ssd512_batch128_sampled():
             eq(r['scores'][b], o['scores'], 'scores')
             eq(r['loc'][b], o['loc'], 'loc')
             eq(r['objness'][b], o['objness'], 'objness')
+
+
+@pytest.mark.parametrize('thr', [0.45, 0.02])
+@pytest.mark.parametrize('tier_k', [1024, 1 << 30])
+def test_crowded_detect_two_tier_topk_batch16(ron, dec_anchors, thr, tier_k, monkeypatch):
+    """BASELINE config 5 shape through the fused detect path at batch 16: 81 classes, dense scores, top_k = 10 000, in
+    one tier (the default) and in two (core.TIER_K = 1024: first 1024 candidates, then the full 10 000 for the rows that
+    ran out before keep_top_k boxes were kept); thr = 0.02 suppresses almost everything, so many rows need the second
+    tier."""
+    from ron_tensorflow_b200 import core
+    monkeypatch.setattr(core, 'TIER_K', tier_k)
+    net, anchors = ron
+    B, C, K, M = 16, 81, 10000, 200
+    loc, pred, obj = synth.make_predictions(5005, B, 21250, C, hot=2000, dense=True)
+    obj = np.maximum(obj, np.float32(0.05))
+    ns, nb, ni = net.detect(_layers(pred, False), _layers(loc, False), _layers(obj, False), 0.03, 0.004, thr, [0., 0., 1., 1.],
+                            K, M, want_idx=True)
+    deep = 0
+    for b in (0, 7, 15):
+        o = O.detected_bboxes_image(pred[b], loc[b], dec_anchors, obj[b], 0.03, 0.004, thr, [0., 0., 1., 1.], K, M)
+        eq(ni[b], o['idx'], 'kept anchor indices b=%d' % b)
+        eq(ns[b], o['scores'], 'scores b=%d' % b)
+        eq(nb[b], o['boxes'], 'boxes b=%d' % b)
+        deep += int((o['nms_pos'].max(1) >= 1024).sum())
+    if thr < 0.1:
+        assert deep > 0, 'the second tier was not exercised'
