@@ -42,7 +42,7 @@ POST_BYTES_PER_IMAGE = N_ANCHORS * (4 * N_CLASSES + 16 + 4) + (N_CLASSES - 1) * 
 def traffic(key):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
     try:
-        v = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json'))).get(key)
+        v = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json'))).get(key)
         return sum(v.values()) if isinstance(v, dict) else v
     except Exception:
         return None

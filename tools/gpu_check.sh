@@ -13,6 +13,9 @@ try:
     print('encode b64  %.1f us  frac %.3f  e2e %.0f img/s' % (d['ms_per_step']*1e3, d['roofline']['frac'], d['e2e']['value']))
     s = d['stages']
     print('encode b256 %.1f us (single %.1f)  frac %.3f' % (s['encode_b256']['ms_per_step']*1e3, s['encode_b256'].get('single_stream_ms_per_step', 0)*1e3, s['encode_b256']['roofline']['frac']))
+    for k in ('ssd512_b128', 'crowded'):
+        for kk, v in (s.get(k) or {}).items():
+            if isinstance(v, dict) and 'value' in v: print('%s.%s %.0f img/s frac %.3f' % (k, kk, v['value'], v['roofline']['frac']))
     if s.get('postprocess'):
         print('post b256   %.1f us  frac %.3f  e2e %.0f img/s' % (s['postprocess']['ms_per_step']*1e3, s['postprocess']['roofline']['frac'], s['postprocess']['e2e']['value']))
     print('cpu', d.get('cpu_baseline'))
@@ -33,5 +36,6 @@ for k, v in sorted(t.items(), key=lambda kv: -sum(kv[1])):
 PY
 if [ "$2" = "full" ]; then
   ncu --set full --clock-control none --import-source on -k regex:match_encode -s 2 -c 1 -o gpurun_out/${tag}_enc python tools/prof.py --stage encode --batch 256 --iters 3 > /dev/null 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:match_encode -s 2 -c 1 -o gpurun_out/${tag}_enc64 python tools/prof.py --stage encode --batch 64 --iters 3 > /dev/null 2>&1
   ncu --set full --clock-control none --import-source on -k 'regex:scatter|pivot|select_topk|nms_kernel|tpfp' -s 6 -c 6 -o gpurun_out/${tag}_post python tools/prof.py --stage post --batch 256 --iters 2 > /dev/null 2>&1
 fi
