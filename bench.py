@@ -344,6 +344,16 @@ def run_ours(args):
     bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        # communicator set-up and the first use of each collective are not part of any timed region
+        w_ = torch.zeros((8,), dtype=torch.int64, device=dev)
+        wo_ = torch.empty((world, 8), dtype=torch.int64, device=dev)
+        dist.all_reduce(w_)
+        dist.all_gather_into_tensor(wo_, w_)
+        w32 = torch.zeros((8,), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(torch.empty((world, 8), dtype=torch.int32, device=dev), w32)
+        wf = torch.zeros((8,), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(torch.empty((world, 8), dtype=torch.float32, device=dev), wf)
+        torch.cuda.synchronize()
     hbm, peak_src = peaks()
 
     def barrier():

@@ -204,11 +204,14 @@ int ronk_tpfp_match(const float* det_scores, const float* det_boxes, int B, int 
  * `records` (uint64 [capacity]: score bits << 32 | class index << 8 | fp << 1 | tp) in (class, image, rank) order
  * behind the earlier batches; n_gt_acc int64 [C-1] accumulates the ground-truth counts.  totals int32 [4] =
  * {count, count, overflow flag, -} must start zeroed; call_parity = number of earlier calls on these buffers (the two
- * count slots alternate between "before" and "after").  Nothing is read back: one copy at the end of the evaluation. */
+ * count slots alternate between "before" and "after"); seg_counts int32 [C-1] (or NULL) receives this call's records per
+ * class, which lets the host cut the class-major batches apart without sorting.  Nothing is read back: one copy at the
+ * end of the evaluation. */
 size_t ronk_tpfp_records_workspace_bytes(int B, int C, int M);
 int ronk_tpfp_records_append(const float* det_scores, const uint8_t* tp, const uint8_t* fp, const int64_t* n_gt,
                              int B, int C, int M, float min_score, uint64_t* records, int capacity,
-                             int32_t* totals, int call_parity, int64_t* n_gt_acc, void* ws, void* stream);
+                             int32_t* totals, int call_parity, int64_t* n_gt_acc, int32_t* seg_counts, void* ws,
+                             void* stream);
 
 /* ------------------------------------------------- fine-grained functions
  * One kernel per small reference function, so the whole Python surface is on the GPU:

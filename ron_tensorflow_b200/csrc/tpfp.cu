@@ -130,6 +130,7 @@ struct RecParams {
     int* totals;
     int slot_in, slot_out;
     long long* n_gt_acc;        // [CM]
+    int* seg_counts;            // [CM] records of this call per class (zeroed before the launch), or NULL
 };
 
 __device__ __forceinline__ bool rec_keep(const RecParams& p, long long e, size_t* src) {
@@ -146,10 +147,18 @@ records_count_kernel(const __grid_constant__ RecParams p) {
     __shared__ int s_w[8];
     const long long base = (long long)blockIdx.x * kRecTile;
     int c = 0;
+    const long long per_class = (long long)p.B * p.M;
     for (int k = threadIdx.x; k < kRecTile; k += 256) {
         const long long e = base + k;
         size_t src;
-        c += (e < p.n && rec_keep(p, e, &src)) ? 1 : 0;
+        const bool keep = e < p.n && rec_keep(p, e, &src);
+        c += keep ? 1 : 0;
+        if (p.seg_counts) {
+            // per-class totals of this call: the 32 elements of a warp step nearly always share one class
+            const int cls = keep ? (int)(e / per_class) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, cls);
+            if (keep && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(p.seg_counts + cls, __popc(peers));
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
@@ -230,7 +239,8 @@ extern "C" size_t ronk_tpfp_records_workspace_bytes(int B, int C, int M) {
 
 extern "C" int ronk_tpfp_records_append(const float* det_scores, const uint8_t* tp, const uint8_t* fp, const int64_t* n_gt,
                                         int B, int C, int M, float min_score, uint64_t* records, int capacity,
-                                        int32_t* totals, int call_parity, int64_t* n_gt_acc, void* ws, void* stream) {
+                                        int32_t* totals, int call_parity, int64_t* n_gt_acc, int32_t* seg_counts, void* ws,
+                                        void* stream) {
     RONK_REQUIRE(det_scores && tp && fp && n_gt && records && totals && n_gt_acc && ws, RONK_EINVAL,
                  "ronk_tpfp_records_append: NULL argument");
     RONK_REQUIRE(B >= 1 && C >= 2 && C <= (1 << 20) && M >= 1 && capacity >= 1, RONK_EINVAL, "ronk_tpfp_records_append: bad sizes");
@@ -247,6 +257,8 @@ extern "C" int ronk_tpfp_records_append(const float* det_scores, const uint8_t* 
     p.slot_in = call_parity & 1;
     p.slot_out = p.slot_in ^ 1;
     p.n_gt_acc = (long long*)n_gt_acc;
+    p.seg_counts = seg_counts;
+    if (seg_counts) RONK_CUDA(cudaMemsetAsync(seg_counts, 0, (size_t)p.CM * 4, (cudaStream_t)stream));
     const unsigned tiles = (unsigned)((p.n + kRecTile - 1) / kRecTile);
     cudaStream_t st = (cudaStream_t)stream;
     records_count_kernel<<<tiles, 256, 0, st>>>(p);

@@ -55,7 +55,7 @@ class TpFpDeviceState(object):
     nothing is read back until ``to_host()`` / ``gather_tp_fp`` at the end of the evaluation -- one copy instead of
     4 x (C - 1) device->host reads per batch.  ``capacity``: records the buffer can hold (an overflow raises at the end)."""
 
-    def __init__(self, num_classes, capacity=1 << 22, device=None):
+    def __init__(self, num_classes, capacity=1 << 22, device=None, max_updates=4096):
         from .. import core
         core._require_cuda()
         self.num_classes = int(num_classes)
@@ -64,6 +64,7 @@ class TpFpDeviceState(object):
         self.records = torch.empty((self.capacity,), dtype=torch.int64, device=self.device)
         self.totals = torch.zeros((4,), dtype=torch.int32, device=self.device)
         self.n_gt = torch.zeros((self.num_classes - 1,), dtype=torch.int64, device=self.device)
+        self.seg = torch.zeros((int(max_updates), self.num_classes - 1), dtype=torch.int32, device=self.device)
         self.calls = 0
         self._ws = None
 
@@ -83,11 +84,14 @@ class TpFpDeviceState(object):
         need = int(L.ronk_tpfp_records_workspace_bytes(B, CM + 1, M))
         if self._ws is None or self._ws.numel() * 4 < need:
             self._ws = torch.empty(((need + 3) // 4,), dtype=torch.int32, device=self.device)
+        if self.calls >= self.seg.shape[0]:
+            raise RuntimeError('TpFpDeviceState: more than %d updates, raise `max_updates`' % self.seg.shape[0])
         p = lambda x: ctypes.c_void_p(x.data_ptr())
         with torch.cuda.device(self.device):
             _ffi.check(L.ronk_tpfp_records_append(p(s.contiguous()), p(t.contiguous()), p(f.contiguous()), p(g.contiguous()), B, CM + 1, M,
                                                   float(min_score), p(self.records), self.capacity, p(self.totals), self.calls & 1,
-                                                  p(self.n_gt), p(self._ws), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                                  p(self.n_gt), p(self.seg[self.calls]), p(self._ws),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.calls += 1
         return self
 
@@ -96,22 +100,29 @@ class TpFpDeviceState(object):
         return self.totals[self.calls & 1]
 
     @staticmethod
-    def _split(records, n_gt, num_classes):
-        """host records (int64 array in arrival order) -> dict class -> TpFpAccumulator (stable per class)."""
-        w = np.ascontiguousarray(records).view(np.uint32).reshape(-1, 2)      # little endian: (meta, score bits)
-        meta, scores = w[:, 0].copy(), w[:, 1].copy().view(np.float32)
-        cls = (meta >> 8).astype(np.uint8 if num_classes <= 256 else (np.uint16 if num_classes <= 65536 else np.int64))
-        order = np.argsort(cls, kind='stable')                    # radix sort for small integers: O(n)
-        bounds = np.concatenate([[0], np.cumsum(np.bincount(cls, minlength=num_classes - 1))])
-        scores, meta = scores[order], meta[order]
+    def _assemble(parts, n_gt, num_classes):
+        """parts: per rank (records int64 [n] in arrival order, seg int32 [updates, C-1]) on the host.  Every update
+        appended its records class after class, so class c of update u is one contiguous run: the per-class arrays
+        are concatenations of runs (rank-major, then update order) -- no sorting.  -> dict class -> TpFpAccumulator."""
+        CM = num_classes - 1
+        runs = [[] for _ in range(CM)]
+        for rec, seg in parts:
+            w = np.ascontiguousarray(rec).view(np.uint32).reshape(-1, 2)          # little endian: (meta, score bits)
+            ends = np.cumsum(seg.reshape(-1).astype(np.int64))
+            starts = ends - seg.reshape(-1)
+            for u in range(seg.shape[0]):
+                for c in range(CM):
+                    k = u * CM + c
+                    if ends[k] > starts[k]:
+                        runs[c].append(w[starts[k]:ends[k]])
         out = {}
         for c in range(1, num_classes):
-            lo, hi = int(bounds[c - 1]), int(bounds[c])
+            blk = np.concatenate(runs[c - 1]) if runs[c - 1] else np.zeros((0, 2), np.uint32)
             acc = TpFpAccumulator()
             acc.n_gt = int(n_gt[c - 1])
-            acc.scores = scores[lo:hi].copy()
-            acc.tp = (meta[lo:hi] & 1).astype(bool)
-            acc.fp = ((meta[lo:hi] >> 1) & 1).astype(bool)
+            acc.scores = blk[:, 1].copy().view(np.float32)
+            acc.tp = (blk[:, 0] & 1).astype(bool)
+            acc.fp = ((blk[:, 0] >> 1) & 1).astype(bool)
             out[c] = acc
         return out
 
@@ -121,7 +132,8 @@ class TpFpDeviceState(object):
         if tot[2]:
             raise RuntimeError('TpFpDeviceState: more than %d records, raise `capacity`' % self.capacity)
         n = int(tot[self.calls & 1])
-        return self._split(self.records[:n].cpu().numpy(), self.n_gt.cpu().numpy(), self.num_classes)
+        return self._assemble([(self.records[:n].cpu().numpy(), self.seg[:self.calls].cpu().numpy())], self.n_gt.cpu().numpy(),
+                              self.num_classes)
 
 
 def streaming_tp_fp_arrays(num_gbboxes, tp, fp, scores, remove_zero_scores=True, metrics_collections=None,
@@ -191,8 +203,11 @@ def gather_tp_fp(state, num_classes, group=None):
         if not multi:
             return state.to_host()
         world = dist.get_world_size(group)
+        CM = state.num_classes - 1
+        # one small all_gather: record count, overflow flag, number of updates of every rank
         meta = torch.cat([state.totals[(state.calls & 1):(state.calls & 1) + 1], state.totals[2:3]]).to(torch.int64)
-        all_meta = torch.empty((world, 2), dtype=torch.int64, device=state.device)
+        meta = torch.cat([meta, torch.tensor([state.calls], dtype=torch.int64, device=state.device)])
+        all_meta = torch.empty((world, 3), dtype=torch.int64, device=state.device)
         dist.all_gather_into_tensor(all_meta, meta, group=group)
         n_gt = state.n_gt.clone()
         dist.all_reduce(n_gt, op=dist.ReduceOp.SUM, group=group)
@@ -200,14 +215,17 @@ def gather_tp_fp(state, num_classes, group=None):
         if all_meta[:, 1].any():
             raise RuntimeError('TpFpDeviceState: a rank ran out of record capacity (%d)' % state.capacity)
         width = max(int(all_meta[:, 0].max()), 1)
-        if width > state.capacity:
-            raise RuntimeError('TpFpDeviceState: capacity %d below the widest rank (%d records)' % (state.capacity, width))
+        calls = max(int(all_meta[:, 2].max()), 1)
+        if width > state.capacity or calls > state.seg.shape[0]:
+            raise RuntimeError('TpFpDeviceState: capacity %d / max_updates %d below the largest rank (%d records, %d updates)'
+                               % (state.capacity, state.seg.shape[0], width, calls))
         out = torch.empty((world, width), dtype=torch.int64, device=state.device)
         dist.all_gather_into_tensor(out, state.records[:width].contiguous(), group=group)
-        host = out.cpu().numpy()
-        rec = np.concatenate([host[r, :int(all_meta[r, 0])] for r in range(world)])
-        # rank-major order per class == stable split of the rank-major concatenation
-        return TpFpDeviceState._split(rec, n_gt.cpu().numpy(), state.num_classes)
+        segs = torch.empty((world, calls, CM), dtype=torch.int32, device=state.device)
+        dist.all_gather_into_tensor(segs, state.seg[:calls].contiguous(), group=group)
+        host, segs = out.cpu().numpy(), segs.cpu().numpy()       # (a pinned staging buffer only pays when it is reused: measured)
+        parts = [(host[r, :int(all_meta[r, 0])], segs[r, :int(all_meta[r, 2])]) for r in range(world)]
+        return TpFpDeviceState._assemble(parts, n_gt.cpu().numpy(), state.num_classes)
     if not multi:
         return state
     world = dist.get_world_size(group)
