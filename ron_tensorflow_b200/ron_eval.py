@@ -51,6 +51,19 @@ def filter_boxes(scores, labels, bboxes, min_size_ratio, image_shape, net_input_
             core.gather_rows(core.as_cuda(labels, torch.int64, b.device), idx), core.gather_rows(b, idx))
 
 
+MAX_SORT = 16384          # ronk_sort_topk: the winners are sorted in shared memory
+MAX_KEEP = 2048           # ronk_nms_batch: the kept list lives in shared memory
+
+
+def _check_limits(n, keep_top_k, what):
+    """The reference's tf.nn.top_k(k = number of boxes) has no upper bound; the kernels behind these functions do."""
+    if n > MAX_SORT:
+        raise ValueError('%s: %d boxes pass FLAGS.select_threshold / objectness_thres, the sort kernel takes at most %d '
+                         '(raise the thresholds, or use the fused RONNet.detect path, which selects per class)' % (what, n, MAX_SORT))
+    if keep_top_k > MAX_KEEP:
+        raise ValueError('%s: keep_top_k = %d, the NMS kernel keeps at most %d boxes per row' % (what, keep_top_k, MAX_KEEP))
+
+
 def tf_bboxes_nms(scores, labels, bboxes, nms_threshold=0.5, keep_top_k=200, mode='union', scope=None):
     """reference ron_eval.py:146-210: class-agnostic greedy NMS on the best class score of every box.
     scores [M,C]; returns the kept (score [k], label [k], box [k,4]) in decreasing score order."""
@@ -65,6 +78,7 @@ def tf_bboxes_nms(scores, labels, bboxes, nms_threshold=0.5, keep_top_k=200, mod
     n = int(best.shape[0])
     if n < 1:                                                                       # tf.cond(num_anchors < 1, ...) :210
         return best, labels, bboxes
+    _check_limits(n, keep_top_k, 'tf_bboxes_nms')
     ss, sb, si = core.sort_topk(best.reshape(1, n), bboxes.reshape(1, n, 4), n, want_idx=True)    # :155-156
     ns, nb, ni = core.nms_batch(ss, sb, nms_threshold, keep_top_k, mode, assume_sorted=True, want_idx=True)
     kept = core.compact_indices((ni[0] >= 0).to(torch.uint8))
@@ -87,6 +101,7 @@ def tf_bboxes_nms_by_class(scores, labels, bboxes, nms_threshold=0.5, keep_top_k
     n = int(s.shape[0])
     if n < 1:                                                                       # tf.cond(num_anchors < 1, ...) :291
         return s, core.as_cuda(labels, torch.int64, s.device), b
+    _check_limits(n, keep_top_k, 'tf_bboxes_nms_by_class')
     cs, cb = core.class_columns(s, b, FLAGS.select_threshold)                      # :228 + the transpose of :277
     ss, sb, si = core.sort_topk(cs, cb, n, want_idx=True)                          # :217-218
     ns, _, ni = core.nms_batch(ss, sb, nms_threshold, keep_top_k, mode, assume_sorted=True, want_idx=True)
@@ -111,6 +126,7 @@ def tf_bboxes_nms_by_class_v1(scores, labels, bboxes, nms_threshold=0.5, keep_to
     n = int(best.shape[0])
     if n < 1:                                                                       # :366
         return best, labels, bboxes
+    _check_limits(n, keep_top_k, 'tf_bboxes_nms_by_class_v1')
     ss, sb, si = core.sort_topk(best.reshape(1, n), bboxes.reshape(1, n, 4), n, want_idx=True)    # :301-302
     sl = core.gather_rows(labels, si[0].contiguous())
     gs, gb, gp = core.group_by_label(sl, ss[0], sb[0], FLAGS.num_classes)          # nms_mask = (labels == cls) :340
