@@ -164,13 +164,12 @@ __device__ __forceinline__ void rect_task(const GridSmem& s, int a, int rows, in
             for (int cc = c0; cc <= c1; cc += 32) {
                 const int c = min(cc + cl, c1);
                 const float4 ct = lds128(col + c * 16);
-                float wx = overlap_1d<NICE>(t.y, t.w, ct.x, ct.y);
-                if (rl >= rpi || cc + cl > c1) wx = 0.f;                    // spare lanes: zero overlap, touch nothing
+                const float wx = overlap_1d<NICE>(t.y, t.w, ct.x, ct.y);
                 const float wA = ct.z;
                 unsigned mymax = 0u;
                 int myr = 0;
-                // lane-divergent trip count: lanes past the last row fall out early
-                int r = r0 + rl;
+                // lane-divergent trip count: lanes past the last row fall out early, spare lanes never enter
+                int r = (rl >= rpi || cc + cl > c1) ? r1 + 1 : r0 + rl;
                 unsigned rp = row + r * 16, sp = plane + (unsigned)(r * W + c) * 8u;
                 for (; r <= r1; r += rpi, rp += rstep, sp += sstep) {
                     const float4 rt = lds128(rp);
