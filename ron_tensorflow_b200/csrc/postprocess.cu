@@ -18,6 +18,10 @@
 #include "common.cuh"
 #include "topk.cuh"
 
+#ifndef RONK_TOPK_MINB
+#define RONK_TOPK_MINB 6   // 40 registers; 8 (32 registers) spills 104 B
+#endif
+
 namespace ronk {
 
 
@@ -631,7 +635,7 @@ __device__ int rebuild_list(const PostParams& p, int b, int c, u64* g, int* s_cn
 //                     the keys >= pivot in shared memory, and the select runs on those.  If the pivot
 //                     turns out too high (fewer than K survivors) or too low (more than 2048), the
 //                     generic 8-bit radix select over the whole list takes over -- always exact.
-__global__ void __launch_bounds__(kTopkThreads, 6)
+__global__ void __launch_bounds__(kTopkThreads, RONK_TOPK_MINB)
 select_topk_kernel(const __grid_constant__ PostParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int P = next_pow2(p.K);
