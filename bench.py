@@ -632,6 +632,24 @@ def run_ours(args):
         torch.cuda.synchronize()
         loop_launches = core.launch_count() - l0
         t_loop = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)
+        # the tail of the evaluation on the device: NCCL all-gather of the packed records (they stay on the device),
+        # stable radix sort by (class, score), float64 precision / recall / AP07 / AP12 of all classes, one read-back
+        # of 2 x 20 doubles.  One untimed pass first (allocations, NCCL channels for these shapes).
+        state.average_precision()
+        torch.cuda.synchronize()
+        barrier()
+        g0 = time.perf_counter()
+        rec_all, ngt_all = tfe.gather_tp_fp_records(state)
+        torch.cuda.synchronize()
+        gather_dev_ms = max_over_ranks(time.perf_counter() - g0) * 1e3
+        l0 = core.launch_count()
+        g0 = time.perf_counter()
+        r_dev = tfe.average_precision_records(rec_all, ngt_all, N_CLASSES)
+        ap_dev = torch.stack([r_dev['ap07'], r_dev['ap12']]).cpu().numpy()
+        ap_dev_ms = max_over_ranks(time.perf_counter() - g0) * 1e3
+        ap_dev_launches = core.launch_count() - l0
+        n_rec_dev = int(r_dev['offsets'][-1].item())
+        del rec_all, r_dev
         barrier()
         g0 = time.perf_counter()
         merged_all = tfe.gather_tp_fp(state, N_CLASSES)
@@ -647,6 +665,11 @@ def run_ours(args):
                      'gpu_launches': loop_launches, 'tpfp_gather_ms': eval_gather_ms, 'detections_gather_ms': det_gather_ms,
                      'detections_gathered_shape': list(all_s.shape), 'wall_ms_loop_plus_gathers': t_total * 1e3,
                      'records': int(sum(merged_all[c].scores.shape[0] for c in cls)), 'backend': 'nccl' if world > 1 else 'none',
+                     'device_tail': {'tpfp_gather_ms': gather_dev_ms, 'ap_ms': ap_dev_ms, 'gpu_launches': ap_dev_launches,
+                                     'records': n_rec_dev,
+                                     'note': 'tfe.gather_tp_fp_records (records stay on the device) + tfe.average_precision_records '
+                                             '(radix sort + AP07 / AP12 of all classes, incl. the read-back of 40 doubles); host '
+                                             'clock, max over ranks; tpfp_gather_ms / ap_host_ms beside it are the host-side path'},
                      'config': {'workload': 'VOC07-test sized evaluation (>= %d images, %d batches of %d per GPU), BASELINE configs[2] '
                                             'post-process parameters, records accumulated on the device (tfe.TpFpDeviceState), one '
                                             'gather of the records (tfe.gather_tp_fp) and one of the last batch of detections '
@@ -660,6 +683,13 @@ def run_ours(args):
                 ap_all.append(tfe.average_precision_voc07(p_, r_))
             eval_loop['ap_host_ms'] = (time.perf_counter() - a0) * 1e3
             eval_loop['mAP_voc07_synthetic'] = float(np.mean(ap_all))
+            if n_rec_dev != eval_loop['records'] or any(ap_dev[0, c - 1] != ap_all[c - 1] for c in cls):
+                raise RuntimeError('bench: device AP07 differs from the host computation')
+            for c in cls:
+                p_, r_ = tfe.precision_recall(*merged_all[c].value())
+                if abs(ap_dev[1, c - 1] - tfe.average_precision_voc12(p_, r_)) > 1e-12:
+                    raise RuntimeError('bench: device AP12 of class %d differs from the host computation' % c)
+            eval_loop['device_tail']['check'] = 'AP07 of all %d classes bit-equal to the host NumPy path, AP12 within 1e-12' % len(cls)
             if world > 1:
                 # the NCCL path against a single-process accumulation of the same shards, rank-major: bit-equal records and AP
                 single = tfe.TpFpDeviceState(N_CLASSES, capacity=cap * world)

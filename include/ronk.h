@@ -213,6 +213,22 @@ int ronk_tpfp_records_append(const float* det_scores, const uint8_t* tp, const u
                              int32_t* totals, int call_parity, int64_t* n_gt_acc, int32_t* seg_counts, void* ws,
                              void* stream);
 
+/* precision_recall + average_precision_voc07 / _voc12 (tf_extended/metrics.py:100-130, :237-258, :212-234; called
+ * from eval_ron_network.py:262-324) on the device-resident records of ronk_tpfp_records_append, all classes in one
+ * call: `records` uint64 [n] in concatenation order (rank-major after an all-gather, batch after batch); an entry whose
+ * class index is 0xffffff is padding and ignored.  A stable radix sort by (class, descending score) reproduces
+ * tf.nn.top_k's tie order (lower index first); cumulative sums are exact integers; precision / recall / the envelope /
+ * the two sums are float64 with the reference's safe division and a fixed reduction order (VOC07 equals the host
+ * NumPy value bit for bit, VOC12 to rounding).  n_gt int64 [C-1] (device).  thresholds: HOST pointer to the
+ * n_thresholds (<= 16) recall levels of VOC07 (np.arange(0., 1.1, 0.1) in the reference).  Outputs (device):
+ * out_ap07 / out_ap12 float64 [C-1]; optional out_offsets int32 [C] (first sorted record of every class, then the
+ * number of real records), out_sorted uint64 [n], out_precision / out_recall float64 [n] (sorted order). */
+size_t ronk_average_precision_workspace_bytes(long long n, int C);
+int ronk_average_precision_records(const uint64_t* records, long long n, const int64_t* n_gt, int C,
+                                   const double* thresholds, int n_thresholds, double* out_ap07, double* out_ap12,
+                                   int32_t* out_offsets, uint64_t* out_sorted, double* out_precision,
+                                   double* out_recall, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------- fine-grained functions
  * One kernel per small reference function, so the whole Python surface is on the GPU:
  * ronk_areas            areas                      nets/ssd_common.py:27-29     boxes [n,4] -> [n]

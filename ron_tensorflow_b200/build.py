@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libronk.so')
-SOURCES = ['api.cu', 'anchors.cu', 'match_encode.cu', 'match_encode_grid.cu', 'postprocess.cu', 'nms.cu', 'tpfp.cu', 'misc.cu', 'roneval.cu', 'losses.cu', 'npmethods.cu', 'voceval.cu', 'hostpath.cu']
+SOURCES = ['api.cu', 'anchors.cu', 'match_encode.cu', 'match_encode_grid.cu', 'postprocess.cu', 'nms.cu', 'tpfp.cu', 'ap.cu', 'misc.cu', 'roneval.cu', 'losses.cu', 'npmethods.cu', 'voceval.cu', 'hostpath.cu']
 HEADERS = ['common.cuh', 'encode_common.cuh', 'topk.cuh', os.path.join('..', '..', 'include', 'ronk.h')]
 
 # -fmad=false: one rounding per float op (parity with one TF op per node); IEEE div/sqrt are

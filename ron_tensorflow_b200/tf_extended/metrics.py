@@ -13,7 +13,11 @@ import numpy as np
 import torch
 
 __all__ = ['streaming_tp_fp_arrays', 'precision_recall', 'average_precision_voc07', 'average_precision_voc12',
-           'TpFpAccumulator', 'TpFpDeviceState', 'gather_tp_fp', 'gather_detections']
+           'TpFpAccumulator', 'TpFpDeviceState', 'gather_tp_fp', 'gather_detections', 'average_precision_records',
+           'gather_tp_fp_records', 'PAD_RECORD']
+
+# a record whose class index is 0xffffff is padding: ronk_average_precision_records sorts it behind every class and ignores it
+PAD_RECORD = 0xffffff << 8
 
 
 def _np(x):
@@ -126,6 +130,22 @@ class TpFpDeviceState(object):
             out[c] = acc
         return out
 
+    def average_precision(self, group=None, curves=False):
+        """AP of every class without moving the records to the host: the records of all ranks are all-gathered on the
+        device (``gather_tp_fp_records``; a no-op without a process group) and ``average_precision_records`` sorts and
+        integrates them there.  Returns ``(ap07, ap12)``: dicts class -> float, read back in one copy of 2 x (C - 1)
+        doubles (with ``curves=True`` a third value: dict class -> (precision, recall) float64 device tensors)."""
+        rec, n_gt = gather_tp_fp_records(self, group)
+        r = average_precision_records(rec, n_gt, self.num_classes, curves=curves)
+        both = torch.stack([r['ap07'], r['ap12']]).cpu().numpy()
+        ap07 = {c: float(both[0, c - 1]) for c in range(1, self.num_classes)}
+        ap12 = {c: float(both[1, c - 1]) for c in range(1, self.num_classes)}
+        if not curves:
+            return ap07, ap12
+        off = r['offsets'].cpu().numpy()
+        cur = {c: (r['precision'][off[c - 1]:off[c]], r['recall'][off[c - 1]:off[c]]) for c in range(1, self.num_classes)}
+        return ap07, ap12, cur
+
     def to_host(self):
         """dict class -> TpFpAccumulator (the state ``streaming_tp_fp_arrays`` would have built), one device->host copy."""
         tot = self.totals.cpu().numpy()
@@ -188,6 +208,78 @@ def average_precision_voc07(precision, recall, name=None):
     for t in np.arange(0., 1.1, 0.1):
         ap = ap + np.max(p[r >= t]) / 11.
     return float(ap)
+
+
+def average_precision_records(records, n_gt, num_classes, thresholds=None, curves=False):
+    """precision_recall + average_precision_voc07 / _voc12 (reference :100-130, :237-258, :212-234) of every class in one
+    call, on the device: ``records`` int64 [n] = the packed (score bits << 32 | class index << 8 | fp << 1 | tp) records
+    of ``TpFpDeviceState`` in concatenation order (``PAD_RECORD`` entries are ignored), ``n_gt`` int64 [C-1].  A stable
+    radix sort by (class, descending score) gives tf.nn.top_k's order (lower index first among equal scores); sums and
+    quotients are the reference's float64 ones.  -> dict(ap07, ap12: float64 [C-1] device tensors, offsets int32 [C];
+    with ``curves``: sorted int64 [n], precision / recall float64 [n] in sorted order, class c at offsets[c-1]:offsets[c])."""
+    import ctypes
+    from .. import _ffi, core
+    core._require_cuda()
+    rec = records if (isinstance(records, torch.Tensor) and records.is_cuda) else core.as_cuda(records, torch.int64)
+    rec = rec.contiguous().view(-1)
+    if rec.dtype != torch.int64:
+        raise ValueError('records must be int64 (packed uint64 bit patterns)')
+    dev = rec.device
+    g = core.as_cuda(n_gt, torch.int64, dev).contiguous()
+    C = int(num_classes)
+    if g.numel() != C - 1:
+        raise ValueError('n_gt must have num_classes - 1 entries')
+    n = int(rec.numel())
+    thr = np.arange(0., 1.1, 0.1) if thresholds is None else np.asarray(thresholds, np.float64).reshape(-1)
+    thr_c = (ctypes.c_double * len(thr))(*[float(t) for t in thr])
+    L = _ffi.lib()
+    need = int(L.ronk_average_precision_workspace_bytes(n, C))
+    ws = torch.empty(((need + 7) // 8,), dtype=torch.int64, device=dev)
+    out = dict(ap07=torch.empty((C - 1,), dtype=torch.float64, device=dev), ap12=torch.empty((C - 1,), dtype=torch.float64, device=dev),
+               offsets=torch.empty((C,), dtype=torch.int32, device=dev))
+    if curves:
+        out['sorted'] = torch.empty((n,), dtype=torch.int64, device=dev)
+        out['precision'] = torch.zeros((n,), dtype=torch.float64, device=dev)     # (padding entries stay 0)
+        out['recall'] = torch.zeros((n,), dtype=torch.float64, device=dev)
+    p = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
+    with torch.cuda.device(dev):
+        _ffi.check(L.ronk_average_precision_records(ctypes.c_void_p(rec.data_ptr()) if n else None, n, ctypes.c_void_p(g.data_ptr()), C,
+                                                    thr_c, len(thr), p('ap07'), p('ap12'), p('offsets'), p('sorted'),
+                                                    p('precision'), p('recall'), ctypes.c_void_p(ws.data_ptr()), need,
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
+def gather_tp_fp_records(state, group=None):
+    """The device-resident half of ``gather_tp_fp``: all-gather the packed records of every rank's ``TpFpDeviceState``
+    (NCCL: one small all_gather of the counts, one all_gather_into_tensor of the records, one all_reduce of the
+    ground-truth counts) and leave them on the device.  -> (records int64 [world * width] rank-major, the unused tail of
+    every rank's row set to ``PAD_RECORD``; n_gt int64 [C-1]).  Without a process group: this rank's own records."""
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    par = state.calls & 1
+    if not multi:
+        tot = state.totals.cpu().numpy()
+        if tot[2]:
+            raise RuntimeError('TpFpDeviceState: more than %d records, raise `capacity`' % state.capacity)
+        return state.records[:int(tot[par])], state.n_gt
+    world = dist.get_world_size(group)
+    meta = torch.stack([state.totals[par], state.totals[2]]).to(torch.int64)
+    all_meta = torch.empty((world, 2), dtype=torch.int64, device=state.device)
+    dist.all_gather_into_tensor(all_meta, meta, group=group)
+    n_gt = state.n_gt.clone()
+    dist.all_reduce(n_gt, op=dist.ReduceOp.SUM, group=group)
+    host_meta = all_meta.cpu().numpy()                       # the one sync: the width of the gather
+    if host_meta[:, 1].any():
+        raise RuntimeError('TpFpDeviceState: a rank ran out of record capacity (%d)' % state.capacity)
+    width = max(int(host_meta[:, 0].max()), 1)
+    if width > state.capacity:
+        raise RuntimeError('TpFpDeviceState: capacity %d below the largest rank (%d records)' % (state.capacity, width))
+    out = torch.empty((world, width), dtype=torch.int64, device=state.device)
+    dist.all_gather_into_tensor(out, state.records[:width].contiguous(), group=group)
+    valid = torch.arange(width, device=state.device)[None, :] < all_meta[:, :1]
+    out = torch.where(valid, out, torch.full((), PAD_RECORD, dtype=torch.int64, device=state.device))
+    return out.view(-1), n_gt
 
 
 def gather_tp_fp(state, num_classes, group=None):

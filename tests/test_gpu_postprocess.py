@@ -418,6 +418,102 @@ def test_device_tpfp_state_matches_host_accumulation():
         small.to_host()
 
 
+def _pack_records(cls, scores, tp, fp):
+    return ((scores.astype(np.float32).view(np.uint32).astype(np.int64) << 32) | (cls.astype(np.int64) << 8) |
+            (fp.astype(np.int64) << 1) | tp.astype(np.int64))
+
+
+def _oracle_ap(cls, scores, tp, fp, n_gt, C):
+    out = {}
+    for c in range(1, C):
+        m = cls == c - 1
+        prec, rec = O.precision_recall(int(n_gt[c - 1]), tp[m], fp[m], scores[m])
+        out[c] = (prec, rec, O.average_precision_voc07(prec, rec), O.average_precision_voc12(prec, rec))
+    return out
+
+
+@pytest.mark.parametrize('case', ['random', 'ties', 'large', 'sparse_classes', 'many_classes'])
+def test_average_precision_records_vs_oracle(case):
+    """tfe.average_precision_records (device: stable radix sort + per-class float64 curves) against the oracle's
+    precision_recall / average_precision_voc07 / _voc12 (tf_extended/metrics.py:100-130, :212-258) class by class:
+    precision and recall arrays bit-equal (exact integer sums, IEEE float64 quotients), VOC07 bit-equal, VOC12 to
+    1e-12 (NumPy sums pairwise, the kernel tile by tile).  Cases: heavy score ties with mixed tp / fp (tf.nn.top_k's
+    lower-index-first order decides), more records than one sort tile / AP tile, classes without records, classes
+    without ground truth, padding entries, more than 255 classes (two class passes of the sort)."""
+    need_cuda()
+    import torch
+    import ron_tensorflow_b200.tf_extended as tfe
+    rng = np.random.Generator(np.random.PCG64({'random': 1, 'ties': 2, 'large': 3, 'sparse_classes': 4, 'many_classes': 5}[case]))
+    C, n = {'random': (21, 5000), 'ties': (5, 6000), 'large': (4, 200000), 'sparse_classes': (12, 3000), 'many_classes': (301, 20000)}[case]
+    cls = rng.integers(0, C - 1, size=n)
+    if case == 'sparse_classes':
+        cls = rng.choice(np.array([0, 3, 4, 10]), size=n)                      # classes 2, 3, 6.. have no record at all
+    scores = rng.uniform(1.1e-4, 1., size=n).astype(np.float32)
+    if case == 'ties':
+        scores = rng.choice(np.array([0.9, 0.5, 0.5000001, 0.25, 2e-4], np.float32), size=n)
+    tp = rng.uniform(size=n) < 0.35
+    fp = ~tp
+    both = rng.uniform(size=n) < 0.02
+    tp, fp = tp | both, fp | both                                              # (the matcher never sets both; the sums must not care)
+    n_gt = rng.integers(1, max(2, n // (C - 1)), size=C - 1).astype(np.int64)
+    if case in ('sparse_classes', 'random'):
+        n_gt[0] = 0                                                            # recall = safe_div -> 0 everywhere
+    rec = _pack_records(cls, scores, tp, fp)
+    # padding entries in the middle and at the end (what the all-gather leaves behind a short rank)
+    pad = np.full((37,), tfe.PAD_RECORD, np.int64) | (np.int64(0x3f000000) << 32)
+    rec_in = np.concatenate([rec[:n // 3], pad, rec[n // 3:], pad[:5]])
+    r = tfe.average_precision_records(torch.from_numpy(rec_in).cuda(), torch.from_numpy(n_gt).cuda(), C, curves=True)
+    torch.cuda.synchronize()
+    off = r['offsets'].cpu().numpy()
+    assert off[0] == 0 and off[-1] == n
+    want = _oracle_ap(cls, scores, tp, fp, n_gt, C)
+    prec, recall = r['precision'].cpu().numpy(), r['recall'].cpu().numpy()
+    srt = r['sorted'].cpu().numpy()
+    ap07, ap12 = r['ap07'].cpu().numpy(), r['ap12'].cpu().numpy()
+    for c in range(1, C):
+        a, b = off[c - 1], off[c]
+        m = cls == c - 1
+        assert b - a == int(m.sum()), c
+        o = O.topk_stable(scores[m], int(m.sum()))
+        eq(srt[a:b], rec[m][o], 'sorted records of class %d' % c)
+        eq(prec[a:b], want[c][0], 'precision of class %d' % c)
+        eq(recall[a:b], want[c][1], 'recall of class %d' % c)
+        assert ap07[c - 1] == want[c][2], (c, ap07[c - 1], want[c][2])
+        assert abs(ap12[c - 1] - want[c][3]) <= 1e-12 * max(1., abs(want[c][3])), (c, ap12[c - 1], want[c][3])
+    # no records at all
+    z = tfe.average_precision_records(torch.zeros((0,), dtype=torch.int64, device='cuda'), torch.from_numpy(n_gt).cuda(), C)
+    assert float(z['ap07'].abs().sum()) == 0. and float(z['ap12'].abs().sum()) == 0.
+
+
+def test_device_state_average_precision_matches_host():
+    """TpFpDeviceState.average_precision() (records never leave the device) equals precision_recall + AP of the host
+    accumulators of tfe.streaming_tp_fp_arrays over several batches."""
+    need_cuda()
+    import torch
+    import ron_tensorflow_b200.tf_extended as tfe
+    rng = np.random.Generator(np.random.PCG64(12))
+    C = 21
+    dev_state = tfe.TpFpDeviceState(C, capacity=1 << 18)
+    host_state = None
+    for B, M in ((8, 200), (3, 200), (16, 200)):
+        sc = np.round(rng.uniform(0, 1, size=(B, C - 1, M)), 2).astype(np.float32)      # two decimals: many equal scores
+        sc[rng.uniform(size=sc.shape) < 0.3] = 0.
+        tp = rng.uniform(size=sc.shape) < 0.2
+        fp = (~tp) & (rng.uniform(size=sc.shape) < 0.7)
+        ng = rng.integers(0, 9, size=(B, C - 1)).astype(np.int64)
+        dev_state.update(*[torch.from_numpy(x).cuda() for x in (ng, tp, fp, sc)])
+        _, host_state = tfe.streaming_tp_fp_arrays({c: ng[:, c - 1] for c in range(1, C)}, {c: tp[:, c - 1] for c in range(1, C)},
+                                                   {c: fp[:, c - 1] for c in range(1, C)}, {c: sc[:, c - 1] for c in range(1, C)},
+                                                   state=host_state)
+    ap07, ap12, curves = dev_state.average_precision(curves=True)
+    for c in range(1, C):
+        p_, r_ = tfe.precision_recall(*host_state[c].value())
+        eq(curves[c][0].cpu().numpy(), p_, 'precision of class %d' % c)
+        eq(curves[c][1].cpu().numpy(), r_, 'recall of class %d' % c)
+        assert ap07[c] == tfe.average_precision_voc07(p_, r_)
+        assert abs(ap12[c] - tfe.average_precision_voc12(p_, r_)) <= 1e-12
+
+
 def test_filter_min_pad_axis_safe_divide(golden):
     """RONNet.bboxes_filter_min stand-alone (tensor and dict forms, nets/ron_vgg_320.py:196-233), tfe.pad_axis and
     tfe.safe_divide against vectors recorded from the reference's own functions; then the batched form (every image of a
