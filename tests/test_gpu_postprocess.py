@@ -1,6 +1,7 @@
 """CUDA decode / select / top-k / NMS / TP-FP against the oracle and the golden vectors.
 Bar: bit-exact kept-box indices, order, scores and boxes."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -616,3 +617,18 @@ def test_crowded_detect_two_tier_topk_batch16(ron, dec_anchors, thr, tier_k, mon
         deep += int((o['nms_pos'].max(1) >= 1024).sum())
     if thr < 0.1:
         assert deep > 0, 'the second tier was not exercised'
+
+
+def test_device_average_precision_over_nccl():
+    """Two ranks with different record counts: NCCL gather that keeps the records on the device (padding marked) +
+    device AP equals the host gather + NumPy AP on every rank (tools/nccl_ap_check.py under torchrun).  Needs 2 GPUs."""
+    need_cuda()
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29533', os.path.join(root, 'tools', 'nccl_ap_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'nccl_ap_check OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
