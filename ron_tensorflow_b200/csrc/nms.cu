@@ -12,6 +12,7 @@
 // walk stops as soon as M boxes are kept.  overlap = inter / min(area_j, area_i) ('min',
 // the reference default) or inter / ((area_j - inter) + area_i) ('union'), safe_divide
 // (0 when the denominator is <= 0), keep test is strict: overlap < threshold.
+#include <stdlib.h>
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -188,6 +189,139 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     }
 }
 
+// Few segments with long candidate lists (crowded scenes: S ~ 1 000, K in the thousands): one warp per segment leaves
+// the machine at ~10 % occupancy and every chunk walks the whole kept list on one warp.  Here a CTA of W warps owns a
+// segment: all warps hold the same chunk of 32 candidates (lane = candidate), warp w tests it against every W-th group of
+// 8 kept boxes, the per-warp verdicts are OR-ed through shared memory, and warp 0 resolves the chunk and appends to the
+// (shared) kept list exactly as nms_kernel does.  Same results: which kept box suppresses a candidate does not matter.
+template <int W>
+__global__ void __launch_bounds__(W * 32)
+nms_wide_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned s_dead[W], s_unc[W];
+    __shared__ int s_count;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = blockIdx.x;
+    if (p.only_flagged && !p.only_flagged[seg]) return;
+    float4* s_kbox = reinterpret_cast<float4*>(smem);
+    float4* s_cbox = s_kbox + p.M + kNmsPad;
+    float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
+    float* s_cvol = s_kvol + p.M;
+    float* s_kt = s_cvol + 32;
+    for (int i = threadIdx.x; i < p.M + kNmsPad; i += W * 32) {
+        s_kbox[i] = make_float4(2.f, 2.f, -1.f, -1.f);
+        s_kt[i] = __int_as_float(0x7f800000);
+    }
+    __syncthreads();
+    bool unit = (p.mode == RONK_NMS_MIN) && (p.thr > 0.f);
+    const bool zero_supp = !(0.f < p.thr);
+    const size_t in0 = (size_t)seg * p.K, out0 = (size_t)seg * p.M;
+    int count = 0;
+    for (int c0 = 0; c0 < p.K && count < p.M; c0 += 32) {
+        const int j = c0 + lane;
+        const bool valid = j < p.K;
+        int pos = -1;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f;
+        if (valid) {
+            pos = p.order ? p.order[in0 + j] : j;
+            box = p.boxes[in0 + pos];
+            score = p.scores[in0 + pos];
+        }
+        const float vol = (box.w - box.y) * (box.z - box.x);
+        bool dead = !valid;
+        bool unclear = false;
+        unit = unit && __all_sync(full, box.x >= 0.f && box.y >= 0.f && box.z <= 1.f && box.w <= 1.f &&
+                                            box.x <= 1.f && box.y <= 1.f && box.z >= 0.f && box.w >= 0.f);
+        if (unit) {
+            const float tj = p.thr * vol;
+            const float tolj = tj * 1e-6f;
+            for (int i0 = warp * kNmsPad; i0 < count; i0 += W * kNmsPad) {
+#pragma unroll
+                for (int i = 0; i < kNmsPad; ++i) {
+                    const float4 kb = s_kbox[i0 + i];
+                    const float kt = s_kt[i0 + i];
+                    const float h = __saturatef(fminf(box.z, kb.z) - fmaxf(box.x, kb.x));
+                    const float w = __saturatef(fminf(box.w, kb.w) - fmaxf(box.y, kb.y));
+                    const float d = h * w - fminf(tj, kt);
+                    dead |= d > 0.f;
+                    unclear |= fabsf(d) <= tolj;
+                }
+                if (__all_sync(full, dead)) break;
+            }
+            if (valid && !(vol > 0.f)) { dead = false; unclear = false; }
+        } else {
+            for (int i0 = warp * 8; i0 < count; i0 += W * 8) {
+                const int lim = min(8, count - i0);
+#pragma unroll 4
+                for (int i = 0; i < lim; ++i) {
+                    const float4 kb = s_kbox[i0 + i];
+                    const float kv = s_kvol[i0 + i];
+                    const float h = fmaxf(fminf(box.z, kb.z) - fmaxf(box.x, kb.x), 0.f);
+                    const float w = fmaxf(fminf(box.w, kb.w) - fmaxf(box.y, kb.y), 0.f);
+                    const float inner = h * w;
+                    const float den = (p.mode == RONK_NMS_UNION) ? ((vol - inner) + kv) : fminf(vol, kv);
+                    const float t = p.thr * den;
+                    const float d = inner - t;
+                    const bool posd = den > 0.f;
+                    dead |= posd ? (d > 0.f) : zero_supp;
+                    unclear |= posd && !(fabsf(d) > t * 1e-6f);
+                }
+                if (__all_sync(full, dead)) break;
+            }
+        }
+        const unsigned dm = __ballot_sync(full, dead), um = __ballot_sync(full, unclear && valid);
+        if (lane == 0) { s_dead[warp] = dm; s_unc[warp] = um; }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned dall = 0u, uall = 0u;
+#pragma unroll
+            for (int w = 0; w < W; ++w) { dall |= s_dead[w]; uall |= s_unc[w]; }
+            dead = (dall >> lane) & 1u;
+            if (unit && valid && !(vol > 0.f)) dead = false;          // an empty candidate overlaps nothing (as above)
+            if (uall) {
+                dead = !valid;
+                for (int i = 0; i < count; ++i)
+                    dead |= suppresses(box, vol, s_kbox[i], s_kvol[i], p.mode, p.thr, zero_supp);
+            }
+            s_cbox[lane] = box;
+            s_cvol[lane] = vol;
+            __syncwarp();
+            unsigned alive_mask = __ballot_sync(full, !dead);
+            unsigned kept = 0u;
+            int room = p.M - count;
+            while (alive_mask && room > 0) {
+                const int i = __ffs(alive_mask) - 1;
+                kept |= 1u << i;
+                --room;
+                const float4 kb = s_cbox[i];
+                const float kv = s_cvol[i];
+                if (lane > i && !dead) dead = suppresses(box, vol, kb, kv, p.mode, p.thr, zero_supp);
+                alive_mask = __ballot_sync(full, !dead) & ~((2u << i) - 1u);
+            }
+            if ((kept >> lane) & 1u) {
+                const int r = count + __popc(kept & ((1u << lane) - 1u));
+                s_kbox[r] = box;
+                s_kvol[r] = vol;
+                s_kt[r] = (vol > 0.f) ? p.thr * vol : __int_as_float(0x7f800000);
+                p.out_scores[out0 + r] = score;
+                p.out_boxes[out0 + r] = box;
+                if (p.out_idx) p.out_idx[out0 + r] = pos;
+            }
+            if (lane == 0) s_count = count + __popc(kept);
+        }
+        __syncthreads();
+        count = s_count;
+    }
+    if (p.out_short && threadIdx.x == 0) p.out_short[seg] = count < p.M ? 1 : 0;
+    for (int r = count + (int)threadIdx.x; r < p.M; r += W * 32) {
+        p.out_scores[out0 + r] = 0.f;
+        p.out_boxes[out0 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.out_idx) p.out_idx[out0 + r] = -1;
+    }
+}
+
 // stable descending order of every row (tf.nn.top_k(k = row length), bboxes.py:179-180)
 struct RowSrc {
     const float* g;
@@ -276,6 +410,23 @@ static int nms_launch(const float* scores, const float* boxes, int S, int K, flo
     size_t smem = (size_t)kNmsWarps * (size_t)nms_smem_per_warp(keep_top_k);
     if (smem > 48 * 1024)
         RONK_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // few segments with long lists: a CTA per segment (nms_wide_kernel).  RONK_NMS_WIDE=0 / 4 / 8 overrides.
+    int wide = (K >= 1024 && S <= 16 * 148) ? 4 : 0;
+    if (const char* e = getenv("RONK_NMS_WIDE")) wide = atoi(e);
+    if (wide == 4 || wide == 8) {
+        const size_t smem_w = (size_t)nms_smem_per_warp(keep_top_k);
+        if (wide == 4) {
+            if (smem_w > 48 * 1024)
+                RONK_CUDA(cudaFuncSetAttribute(nms_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            nms_wide_kernel<4><<<S, 128, smem_w, st>>>(p);
+        } else {
+            if (smem_w > 48 * 1024)
+                RONK_CUDA(cudaFuncSetAttribute(nms_wide_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            nms_wide_kernel<8><<<S, 256, smem_w, st>>>(p);
+        }
+        RONK_LAUNCHED();
+        return RONK_OK;
+    }
     nms_kernel<<<(S + kNmsWarps - 1) / kNmsWarps, kNmsWarps * 32, smem, st>>>(p);
     RONK_LAUNCHED();
     return RONK_OK;

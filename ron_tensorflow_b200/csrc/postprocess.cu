@@ -15,6 +15,7 @@
 //     bitonic sort, box re-decode of the K winners.
 #include <math.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -604,7 +605,7 @@ __device__ int rebuild_list(const PostParams& p, int b, int c, u64* g, int* s_cn
     __syncthreads();
     for (int l = 0; l < p.tab.L; ++l) {
         const int n_l = p.tab.offs[l + 1] - p.tab.offs[l];
-        for (int i0 = 0; i0 < n_l; i0 += kTopkThreads) {
+        for (int i0 = 0; i0 < n_l; i0 += (int)blockDim.x) {
             const int i = i0 + tid;
             bool sel = false;
             float v = 0.f;
@@ -742,6 +743,265 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
             box = p.boxes[(size_t)b * p.tab.N + idx];
         }
         size_t o = (size_t)seg * p.K + r;
+        p.out_scores[o] = sc;
+        p.out_boxes[o] = box;
+        if (p.out_idx) p.out_idx[o] = idx;
+    }
+}
+
+// ------------------------------------------------------------------ large top_k (crowded scenes: K in the thousands)
+// One CTA of 1024 threads per (image, class).  The K winners are found by an 8-bit MSD radix select over the key list in
+// global memory (L2 resident), gathered into shared memory and sorted there by a stable LSD radix sort (8-bit digits,
+// ping-pong between two K-key buffers; a pass whose byte is the same for every key -- the high bytes of ~anchor -- is
+// skipped) instead of a bitonic network over next_pow2(K) keys: 6 passes of K keys against 105 compare-exchange stages
+// of 16 384 for K = 10 000.  Same outputs, same pivot verification / exact rebuild as select_topk_kernel.
+constexpr int kLargeThreads = 1024;
+constexpr int kLargeWarps = kLargeThreads / 32;
+
+// K-th largest of the n distinct keys g[0..n) (n > K): MSD radix select, 8-bit digits, histogram in shared memory
+__device__ u64 large_kth(const u64* g, int n, int K, unsigned* s_hist, int* s_ctl) {
+    const int tid = threadIdx.x;
+    u64 prefix = 0ull, mask = 0ull;
+    int need = K;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (tid < 256) s_hist[tid] = 0u;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += kLargeThreads) {
+            const int i = i0 + tid;
+            bool act = false;
+            unsigned d = 0u;
+            if (i < n) {
+                const u64 k = g[i];
+                act = (k & mask) == prefix;
+                d = (unsigned)(k >> shift) & 255u;
+            }
+            const unsigned amask = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const unsigned peers = __match_any_sync(amask, d);
+                if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[d], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane l owns digits [255 - 8l - 7, 255 - 8l]: find the digit d with (#keys with a larger digit) < need <= that + hist[d]
+            unsigned c[8];
+            unsigned sum = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c[q] = s_hist[255 - (tid * 8 + q)]; sum += c[q]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += v;
+            }
+            unsigned above = incl - sum;
+            if (above < (unsigned)need && (unsigned)need <= incl) {
+                bool done = false;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (!done && (unsigned)need <= above + c[q]) {
+                        s_ctl[0] = 255 - (tid * 8 + q);
+                        s_ctl[1] = need - (int)above;
+                        s_ctl[2] = (c[q] == (unsigned)need - above) ? 1 : 0;
+                        done = true;
+                    } else if (!done) {
+                        above += c[q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (u64)(unsigned)s_ctl[0] << shift;
+        mask |= 255ull << shift;
+        need = s_ctl[1];
+        const int whole = s_ctl[2];
+        __syncthreads();
+        if (whole) break;                       // every key of that bin is a winner: keys >= prefix are exactly the K largest
+    }
+    return prefix;
+}
+
+// lanes of the warp whose 8-bit digit equals this lane's (among the lanes of `among`): eight ballots instead of
+// match.any, whose latency dominated the first version of this sort
+__device__ __forceinline__ unsigned same_digit_lanes(unsigned d, unsigned among) {
+    unsigned peers = among;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool one = (d >> bit) & 1u;
+        const unsigned bm = __ballot_sync(0xffffffffu, one);
+        peers &= one ? bm : ~bm;
+    }
+    return peers;
+}
+
+// a[0..m) -> sorted descending (result pointer returned: a or b), stable LSD radix sort on the bytes that differ.
+// The histogram of a pass is accumulated while the previous pass scatters (plain shared-memory atomics).
+__device__ u64* large_sort_desc(u64* a, u64* b, int m, unsigned* s_total, unsigned* s_base, unsigned short* s_wcnt,
+                                int* s_ctl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    // bytes that are the same in every key need no pass: OR / AND of all keys
+    unsigned* s_red = reinterpret_cast<unsigned*>(s_ctl);       // or_lo, or_hi, and_lo, and_hi
+    if (tid == 0) { s_red[0] = 0u; s_red[1] = 0u; s_red[2] = 0xffffffffu; s_red[3] = 0xffffffffu; }
+    __syncthreads();
+    {
+        unsigned ol = 0u, oh = 0u, al = 0xffffffffu, ah = 0xffffffffu;
+        for (int i = tid; i < m; i += kLargeThreads) {
+            const u64 k = a[i];
+            ol |= (unsigned)k; oh |= (unsigned)(k >> 32);
+            al &= (unsigned)k; ah &= (unsigned)(k >> 32);
+        }
+        ol = __reduce_or_sync(full, ol); oh = __reduce_or_sync(full, oh);
+        al = __reduce_and_sync(full, al); ah = __reduce_and_sync(full, ah);
+        if (lane == 0) { atomicOr(&s_red[0], ol); atomicOr(&s_red[1], oh); atomicAnd(&s_red[2], al); atomicAnd(&s_red[3], ah); }
+    }
+    __syncthreads();
+    const u64 diff = (((u64)s_red[1] << 32) | s_red[0]) ^ (((u64)s_red[3] << 32) | s_red[2]);
+    __syncthreads();
+    if (m < 2 || diff == 0ull) return a;
+    int byte = 0;
+    while (((diff >> (8 * byte)) & 255ull) == 0ull) ++byte;
+    // histogram of the first pass
+    if (tid < 256) s_total[tid] = 0u;
+    __syncthreads();
+    for (int i = tid; i < m; i += kLargeThreads) atomicAdd(&s_total[255u - ((unsigned)(a[i] >> (8 * byte)) & 255u)], 1u);
+    __syncthreads();
+    while (byte < 8) {
+        const int shift = 8 * byte;
+        int next = byte + 1;
+        while (next < 8 && ((diff >> (8 * next)) & 255ull) == 0ull) ++next;
+        const int nshift = 8 * (next & 7);
+        if (tid < 32) {
+            // exclusive prefix over the 256 digits (8 per lane)
+            unsigned c[8];
+            unsigned sum = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { c[q] = s_total[tid * 8 + q]; sum += c[q]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(full, incl, o);
+                if (tid >= o) incl += v;
+            }
+            unsigned run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { s_base[tid * 8 + q] = run; run += c[q]; s_total[tid * 8 + q] = 0u; }
+        }
+        reinterpret_cast<uint4*>(s_wcnt)[tid] = make_uint4(0u, 0u, 0u, 0u);            // 32 x 256 u16 = 1024 x 16 B
+        __syncthreads();
+        for (int i0 = 0; i0 < m; i0 += kLargeThreads) {
+            const int i = i0 + tid;
+            const bool valid = i < m;
+            const u64 k = valid ? a[i] : 0ull;
+            const unsigned d = 255u - ((unsigned)(k >> shift) & 255u);
+            const unsigned peers = same_digit_lanes(d, __ballot_sync(full, valid));
+            const unsigned rank = (unsigned)__popc(peers & ((1u << lane) - 1u));
+            if (valid && rank == 0u) s_wcnt[warp * 256 + d] = (unsigned short)__popc(peers);
+            if (valid && next < 8) atomicAdd(&s_total[255u - ((unsigned)(k >> nshift) & 255u)], 1u);
+            __syncthreads();
+            // exclusive prefix over the 32 warps, two digits (one 32-bit word of two u16) per thread
+            unsigned run = 0u;
+            if (tid < 128) {
+                unsigned* col = reinterpret_cast<unsigned*>(s_wcnt) + tid;
+                unsigned c[kLargeWarps];
+#pragma unroll
+                for (int w = 0; w < kLargeWarps; ++w) c[w] = col[w * 128];
+#pragma unroll
+                for (int w = 0; w < kLargeWarps; ++w) {
+                    col[w * 128] = run;                    // per-half sums stay below 2^16 (<= 1024 keys per round)
+                    run += c[w];
+                }
+            }
+            __syncthreads();
+            if (valid) b[s_base[d] + s_wcnt[warp * 256 + d] + rank] = k;
+            __syncthreads();
+            if (tid < 128) {
+                s_base[2 * tid] += run & 0xffffu;
+                s_base[2 * tid + 1] += run >> 16;
+            }
+            reinterpret_cast<uint4*>(s_wcnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+        }
+        u64* t = a; a = b; b = t;
+        byte = next;
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(kLargeThreads, 1)
+select_topk_large_kernel(const __grid_constant__ PostParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    u64* s_a = reinterpret_cast<u64*>(smem);                                   // K
+    u64* s_b = s_a + p.K;                                                      // K
+    unsigned short* s_wcnt = reinterpret_cast<unsigned short*>(s_b + p.K);      // 32 warps x 256 digits
+    unsigned* s_total = reinterpret_cast<unsigned*>(s_wcnt + kLargeWarps * 256);
+    unsigned* s_base = s_total + 256;
+    __shared__ int s_ctl[4];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.x;
+    if (p.only_flagged && !p.only_flagged[seg]) return;
+    const int CM = p.C - 1;
+    const int b = seg / CM;
+    int n = p.counts[seg];
+    n = n > p.cap ? p.cap : n;
+    u64* g = p.keys + (size_t)seg * p.cap;
+    const float seg_thr = p.thr[seg];
+    const u64* sorted = s_a;
+    int m = 0;
+    for (int attempt = 0;; ++attempt) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        if (n <= p.K) {
+            for (int i = tid; i < n; i += kLargeThreads) {
+                const u64 k = g[i];
+                s_a[i] = k;
+            }
+            m = n;
+        } else if (n <= 2 * p.K) {
+            // the whole list fits in the two sort buffers: one pass over global memory, the select passes read shared
+            // memory, and the winners are compacted in place -- after round r at most 1024 (r + 1) winners exist, so a
+            // write never reaches a key that has not been read yet (reads of a round complete before its writes)
+            for (int i = tid; i < n; i += kLargeThreads) s_a[i] = g[i];
+            __syncthreads();
+            const u64 thr = large_kth(s_a, n, p.K, s_total, s_ctl);
+            for (int i0 = 0; i0 < n; i0 += kLargeThreads) {
+                const int i = i0 + tid;
+                const u64 k = (i < n) ? s_a[i] : 0ull;
+                __syncthreads();
+                warp_append(k >= thr && k != 0ull, k, s_a, p.K, &s_cnt);
+                __syncthreads();
+            }
+            m = p.K;
+        } else {
+            const u64 thr = large_kth(g, n, p.K, s_total, s_ctl);
+            for (int i0 = 0; i0 < n; i0 += kLargeThreads) {
+                const int i = i0 + tid;
+                const u64 k = (i < n) ? g[i] : 0ull;
+                warp_append(k >= thr && k != 0ull, k, s_a, p.K, &s_cnt);
+            }
+            m = p.K;
+        }
+        __syncthreads();
+        sorted = large_sort_desc(s_a, s_b, m, s_total, s_base, s_wcnt, s_ctl);
+        // exact iff no pivot was used, or the K-th winner lies above the pivot (see select_topk_kernel)
+        if (attempt > 0 || !(seg_thr > p.sel_thr)) break;
+        if (m >= p.K && __uint_as_float((unsigned)(sorted[p.K - 1] >> 32)) > seg_thr && !p.force_rebuild) break;
+        __syncthreads();
+        n = rebuild_list(p, b, seg - b * CM + 1, g, &s_cnt);
+        n = n > p.cap ? p.cap : n;
+    }
+    for (int r = tid; r < p.K; r += kLargeThreads) {
+        float sc = 0.f;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        int idx = -1;
+        if (r < m) {
+            const u64 k = sorted[r];
+            sc = __uint_as_float((unsigned)(k >> 32));
+            idx = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
+            box = p.boxes[(size_t)b * p.tab.N + idx];
+        }
+        const size_t o = (size_t)seg * p.K + r;
         p.out_scores[o] = sc;
         p.out_boxes[o] = box;
         if (p.out_idx) p.out_idx[o] = idx;
@@ -889,6 +1149,18 @@ static int fill_post_params(PostParams& p, const char* who, const ronk_anchors_t
 }
 
 static int launch_select_topk(const PostParams& p, size_t segs, cudaStream_t st) {
+    // K beyond the register / rank-merge paths of select_topk_kernel (its fallback is a 16 384-key bitonic network):
+    // the radix-sort kernel, as long as two K-key buffers fit in shared memory.  RONK_TOPK_LARGE=0 keeps the old path.
+    const size_t smem_l = (size_t)2 * p.K * sizeof(u64) + (size_t)kLargeWarps * 256 * 2 + 512 * sizeof(unsigned);
+    bool large = p.K > 4 * kTopkThreads && smem_l <= 220 * 1024;
+    if (const char* e = getenv("RONK_TOPK_LARGE")) large = large && e[0] != '0';
+    if (large) {
+        if (smem_l > 48 * 1024)
+            RONK_CUDA(cudaFuncSetAttribute(select_topk_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+        select_topk_large_kernel<<<(unsigned)segs, kLargeThreads, smem_l, st>>>(p);
+        RONK_LAUNCHED();
+        return RONK_OK;
+    }
     int P = 1;
     while (P < p.K) P <<= 1;
     size_t smem_b = (size_t)(P + kListCap) * sizeof(u64) + (size_t)kBins * sizeof(unsigned);
