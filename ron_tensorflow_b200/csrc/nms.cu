@@ -194,22 +194,26 @@ nms_kernel(const __grid_constant__ NmsParams p) {
 // segment: all warps hold the same chunk of 32 candidates (lane = candidate), warp w tests it against every W-th group of
 // 8 kept boxes, the per-warp verdicts are OR-ed through shared memory, and warp 0 resolves the chunk and appends to the
 // (shared) kept list exactly as nms_kernel does.  Same results: which kept box suppresses a candidate does not matter.
+constexpr int kWidePad = 2 * kNmsPad;      // nms_wide_kernel tests two groups per warp and super-step
+__host__ __device__ constexpr int nms_wide_smem(int M) { return ((M + kWidePad + 32) * 20 + M * 4 + 15) & ~15; }
+
 template <int W>
 __global__ void __launch_bounds__(W * 32)
 nms_wide_kernel(const __grid_constant__ NmsParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned s_dead[W], s_unc[W];
+    __shared__ unsigned s_step[2][W];
     __shared__ int s_count;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg = blockIdx.x;
     if (p.only_flagged && !p.only_flagged[seg]) return;
     float4* s_kbox = reinterpret_cast<float4*>(smem);
-    float4* s_cbox = s_kbox + p.M + kNmsPad;
+    float4* s_cbox = s_kbox + p.M + kWidePad;
     float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
     float* s_cvol = s_kvol + p.M;
     float* s_kt = s_cvol + 32;
-    for (int i = threadIdx.x; i < p.M + kNmsPad; i += W * 32) {
+    for (int i = threadIdx.x; i < p.M + kWidePad; i += W * 32) {
         s_kbox[i] = make_float4(2.f, 2.f, -1.f, -1.f);
         s_kt[i] = __int_as_float(0x7f800000);
     }
@@ -235,20 +239,35 @@ nms_wide_kernel(const __grid_constant__ NmsParams p) {
         unit = unit && __all_sync(full, box.x >= 0.f && box.y >= 0.f && box.z <= 1.f && box.w <= 1.f &&
                                             box.x <= 1.f && box.y <= 1.f && box.z >= 0.f && box.w >= 0.f);
         if (unit) {
+            // super-steps of W x 2 groups of 8 kept boxes: warp w tests groups 2w, 2w + 1 of the super-step, then the
+            // verdicts so far are OR-ed over the warps -- the walk ends as soon as the whole chunk is dead, as it does in
+            // the one-warp kernel, instead of every warp finishing its own slice
             const float tj = p.thr * vol;
             const float tolj = tj * 1e-6f;
-            for (int i0 = warp * kNmsPad; i0 < count; i0 += W * kNmsPad) {
+            int par = 0;
+            for (int s0 = 0; s0 < count; s0 += W * 2 * kNmsPad) {
+                const int i0 = s0 + warp * 2 * kNmsPad;
+                if (i0 < count) {
 #pragma unroll
-                for (int i = 0; i < kNmsPad; ++i) {
-                    const float4 kb = s_kbox[i0 + i];
-                    const float kt = s_kt[i0 + i];
-                    const float h = __saturatef(fminf(box.z, kb.z) - fmaxf(box.x, kb.x));
-                    const float w = __saturatef(fminf(box.w, kb.w) - fmaxf(box.y, kb.y));
-                    const float d = h * w - fminf(tj, kt);
-                    dead |= d > 0.f;
-                    unclear |= fabsf(d) <= tolj;
+                    for (int i = 0; i < 2 * kNmsPad; ++i) {             // entries past `count` are sentinels (list padded by 2 groups)
+                        const float4 kb = s_kbox[i0 + i];
+                        const float kt = s_kt[i0 + i];
+                        const float h = __saturatef(fminf(box.z, kb.z) - fmaxf(box.x, kb.x));
+                        const float w = __saturatef(fminf(box.w, kb.w) - fmaxf(box.y, kb.y));
+                        const float d = h * w - fminf(tj, kt);
+                        dead |= d > 0.f;
+                        unclear |= fabsf(d) <= tolj;
+                    }
                 }
-                if (__all_sync(full, dead)) break;
+                if (s0 + W * 2 * kNmsPad >= count) break;               // last super-step: the ballots below collect it
+                const unsigned dmi = __ballot_sync(full, dead);
+                if (lane == 0) s_step[par][warp] = dmi;
+                __syncthreads();
+                unsigned dall = 0u;
+#pragma unroll
+                for (int w = 0; w < W; ++w) dall |= s_step[par][w];
+                par ^= 1;
+                if (dall == full) { dead = true; break; }               // block-uniform
             }
             if (valid && !(vol > 0.f)) { dead = false; unclear = false; }
         } else {
@@ -414,7 +433,7 @@ static int nms_launch(const float* scores, const float* boxes, int S, int K, flo
     int wide = (K >= 1024 && S <= 16 * 148) ? 4 : 0;
     if (const char* e = getenv("RONK_NMS_WIDE")) wide = atoi(e);
     if (wide == 4 || wide == 8) {
-        const size_t smem_w = (size_t)nms_smem_per_warp(keep_top_k);
+        const size_t smem_w = (size_t)nms_wide_smem(keep_top_k);
         if (wide == 4) {
             if (smem_w > 48 * 1024)
                 RONK_CUDA(cudaFuncSetAttribute(nms_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
