@@ -758,6 +758,19 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
 constexpr int kLargeThreads = 1024;
 constexpr int kLargeWarps = kLargeThreads / 32;
 
+// lanes of the warp whose 8-bit digit equals this lane's (among the lanes of `among`): eight ballots instead of
+// match.any, whose latency dominated the first version of this sort
+__device__ __forceinline__ unsigned same_digit_lanes(unsigned d, unsigned among) {
+    unsigned peers = among;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool one = (d >> bit) & 1u;
+        const unsigned bm = __ballot_sync(0xffffffffu, one);
+        peers &= one ? bm : ~bm;
+    }
+    return peers;
+}
+
 // K-th largest of the n distinct keys g[0..n) (n > K): MSD radix select, 8-bit digits, histogram in shared memory
 __device__ u64 large_kth(const u64* g, int n, int K, unsigned* s_hist, int* s_ctl) {
     const int tid = threadIdx.x;
@@ -776,7 +789,7 @@ __device__ u64 large_kth(const u64* g, int n, int K, unsigned* s_hist, int* s_ct
                 d = (unsigned)(k >> shift) & 255u;
             }
             const unsigned amask = __ballot_sync(0xffffffffu, act);
-            if (act) {
+            if (act) {      // (match.any here: the eight-ballot form measured 7 % slower in this loop, 3 x faster in the sort)
                 const unsigned peers = __match_any_sync(amask, d);
                 if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[d], (unsigned)__popc(peers));
             }
@@ -819,19 +832,6 @@ __device__ u64 large_kth(const u64* g, int n, int K, unsigned* s_hist, int* s_ct
         if (whole) break;                       // every key of that bin is a winner: keys >= prefix are exactly the K largest
     }
     return prefix;
-}
-
-// lanes of the warp whose 8-bit digit equals this lane's (among the lanes of `among`): eight ballots instead of
-// match.any, whose latency dominated the first version of this sort
-__device__ __forceinline__ unsigned same_digit_lanes(unsigned d, unsigned among) {
-    unsigned peers = among;
-#pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
-        const bool one = (d >> bit) & 1u;
-        const unsigned bm = __ballot_sync(0xffffffffu, one);
-        peers &= one ? bm : ~bm;
-    }
-    return peers;
 }
 
 // a[0..m) -> sorted descending (result pointer returned: a or b), stable LSD radix sort on the bytes that differ.
@@ -894,7 +894,7 @@ __device__ u64* large_sort_desc(u64* a, u64* b, int m, unsigned* s_total, unsign
             const bool valid = i < m;
             const u64 k = valid ? a[i] : 0ull;
             const unsigned d = 255u - ((unsigned)(k >> shift) & 255u);
-            const unsigned peers = same_digit_lanes(d, __ballot_sync(full, valid));
+            const unsigned peers = same_digit_lanes(d, __ballot_sync(full, valid));      // (match.any: 1.95 vs 1.70 ms per step)
             const unsigned rank = (unsigned)__popc(peers & ((1u << lane) - 1u));
             if (valid && rank == 0u) s_wcnt[warp * 256 + d] = (unsigned short)__popc(peers);
             if (valid && next < 8) atomicAdd(&s_total[255u - ((unsigned)(k >> nshift) & 255u)], 1u);
