@@ -155,6 +155,13 @@ int ronk_decode_select_topk(const ronk_anchors_t* h,
  */
 int ronk_sort_topk(const float* scores, const float* boxes, int S, int N, int K,
                    float* out_scores, float* out_boxes, int32_t* out_idx, void* stream);
+/* The same per-row tf.nn.top_k(sorted=True) for rows of any length below 2^24 (ronk_sort_topk sorts in shared memory:
+ * K <= 16 384; the reference's tf.nn.top_k(k = number of boxes), ron_eval.py:155 / :217 / :301, has no bound): a stable
+ * LSD radix sort in global memory of one composite key per element (row, descending score, column).  S <= 256, K <= N;
+ * boxes / out_boxes may both be NULL. */
+size_t ronk_sort_rows_workspace_bytes(int S, int N);
+int ronk_sort_rows(const float* scores, const float* boxes, int S, int N, int K, float* out_scores, float* out_boxes,
+                   int32_t* out_idx, void* ws, size_t ws_bytes, void* stream);
 
 /* ----------------------------------------------------------------------- clip
  * Replaces tfe.bboxes_clip (tf_extended/bboxes.py:105-144) on n boxes. */

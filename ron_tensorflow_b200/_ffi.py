@@ -87,6 +87,8 @@ SIGNATURES = {
     'ronk_tpfp_records_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'ronk_tpfp_records_append': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int,
                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ronk_sort_rows_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'ronk_sort_rows': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ronk_average_precision_workspace_bytes': (c_size_t, [c_longlong, c_int]),
     'ronk_average_precision_records': (c_int, [c_void_p, c_longlong, c_void_p, c_int, P(c_double), c_int, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

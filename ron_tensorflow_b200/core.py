@@ -427,6 +427,9 @@ def select_nms(anchors, loc_layers, cls_layers, obj_layers=None, objectness_thre
     return ns.view(B, CM, M), nb.view(B, CM, M, 4), (aidx.view(B, CM, M).int() if want_idx else None)
 
 
+SORT_SHARED_MAX = 16384      # ronk_sort_topk / the unsorted form of ronk_nms_batch sort a row in shared memory
+
+
 def sort_topk(scores, boxes, top_k, want_idx=False):
     """tfe.bboxes_sort on [S,N] / [S,N,4] rows (ronk_sort_topk)."""
     s = as_cuda(scores, torch.float32)
@@ -442,7 +445,15 @@ def sort_topk(scores, boxes, top_k, want_idx=False):
     ob = torch.empty((S, K, 4), dtype=torch.float32, device=s.device)
     oi = torch.empty((S, K), dtype=torch.int32, device=s.device) if want_idx else None
     with torch.cuda.device(s.device):
-        rc = _ffi.lib().ronk_sort_topk(_ptr(s), _ptr(b), S, N, K, _ptr(os_), _ptr(ob), _ptr(oi), _stream())
+        if K > SORT_SHARED_MAX:
+            # beyond the shared-memory sort: radix sort in global memory (the reference's top_k has no bound)
+            L = _ffi.lib()
+            need = int(L.ronk_sort_rows_workspace_bytes(S, N))
+            ws = torch.empty(((need + 7) // 8,), dtype=torch.int64, device=s.device)
+            rc = L.ronk_sort_rows(_ptr(s.contiguous()), _ptr(b.contiguous()), S, N, K, _ptr(os_), _ptr(ob), _ptr(oi), _ptr(ws), need,
+                                  _stream())
+        else:
+            rc = _ffi.lib().ronk_sort_topk(_ptr(s), _ptr(b), S, N, K, _ptr(os_), _ptr(ob), _ptr(oi), _stream())
     _ffi.check(rc)
     return os_, ob, oi
 
@@ -469,6 +480,14 @@ def nms_batch(scores, boxes, nms_threshold=0.5, keep_top_k=200, mode='min', assu
         raise ValueError('expected scores [S,K] and boxes [S,K,4]')
     S, K = int(s.shape[0]), int(s.shape[1])
     M = int(keep_top_k)
+    if not assume_sorted and K > SORT_SHARED_MAX:
+        # rows too long for the in-kernel ordering: sort them first (global-memory radix sort), then the sorted form;
+        # kept indices are mapped back to positions in the caller's rows
+        ss, sb, si = sort_topk(s, b, K, want_idx=True)
+        os_, ob, oi = nms_batch(ss, sb, nms_threshold, M, mode, assume_sorted=True, want_idx=want_idx)
+        if want_idx:
+            oi = torch.where(oi >= 0, torch.gather(si, 1, oi.clamp(min=0).long()).to(torch.int32), oi)
+        return os_, ob, oi
     os_ = torch.empty((S, M), dtype=torch.float32, device=s.device)
     ob = torch.empty((S, M, 4), dtype=torch.float32, device=s.device)
     oi = torch.empty((S, M), dtype=torch.int32, device=s.device) if want_idx else None

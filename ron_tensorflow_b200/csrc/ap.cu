@@ -24,8 +24,10 @@ constexpr int kSortTile = kSortThreads * kSortRounds;      // 8192 records per C
 
 __device__ __forceinline__ unsigned rec_class(u64 r) { return (unsigned)(r & 0xffffffffull) >> 8; }
 
-// passes 0..3: bytes of the inverted score bits (descending score), 4..6: bytes of the class index
+// records (pass < 8): passes 0..3 = bytes of the inverted score bits (descending score), 4..6 = bytes of the class
+// index.  Plain keys (pass >= 8, ronk_sort_rows): byte (pass - 8) of the key, ascending.
 __device__ __forceinline__ unsigned sort_digit(u64 r, int pass) {
+    if (pass >= 8) return (unsigned)(r >> (8 * (pass - 8))) & 255u;
     if (pass < 4) return ((~(unsigned)(r >> 32)) >> (8 * pass)) & 255u;
     return (rec_class(r) >> (8 * (pass - 4))) & 255u;
 }
@@ -453,9 +455,91 @@ static ApLayout ap_layout(long long n, int CM) {
     return L;
 }
 
+// one stable pass of the LSD radix sort: src -> dst by digit `pass`
+static int radix_pass(const u64* src, u64* dst, long long n, int pass, unsigned* hist, int nblocks, cudaStream_t st) {
+    ap_sort_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(src, n, pass, hist, nblocks);
+    RONK_LAUNCHED();
+    ap_scan_u32_kernel<<<1, 1024, 0, st>>>(hist, 256 * nblocks);
+    RONK_LAUNCHED();
+    ap_sort_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(src, dst, n, pass, hist, nblocks);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
+
+// ------------------------------------------------------------------ rows longer than the shared-memory sort takes
+// ronk_sort_rows: tf.nn.top_k(sorted=True) of every row of [S,N] for any N < 2^24: one composite key per element,
+// row << 56 | (0xffffffff - orderable(score)) << 24 | column, sorted ascending by the bytes that can differ.
+__device__ __forceinline__ unsigned rows_orderable(float s) {
+    const unsigned u = __float_as_uint(s + 0.f);          // -0 -> +0: the two zeros tie (lower index first)
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256)
+rows_keys_kernel(const float* __restrict__ scores, int N, long long total, u64* __restrict__ keys) {
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= total) return;
+    const unsigned row = (unsigned)(e / N), col = (unsigned)(e - (long long)row * N);
+    keys[e] = ((u64)row << 56) | ((u64)(0xffffffffu - rows_orderable(scores[e])) << 24) | (u64)col;
+}
+
+__global__ void __launch_bounds__(256)
+rows_gather_kernel(const u64* __restrict__ keys, const float* __restrict__ scores, const float4* __restrict__ boxes, int N,
+                   int K, long long total, float* __restrict__ out_scores, float4* __restrict__ out_boxes,
+                   int* __restrict__ out_idx) {
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;          // (row, rank) of the output
+    if (e >= total) return;
+    const int row = (int)(e / K), r = (int)(e - (long long)row * K);
+    const u64 k = keys[(size_t)row * N + r];
+    const int col = (int)(k & 0xffffffull);
+    const size_t src = (size_t)row * N + col;
+    out_scores[e] = scores[src];
+    if (out_boxes) out_boxes[e] = boxes[src];
+    if (out_idx) out_idx[e] = col;
+}
+
 }  // namespace ronk
 
 using namespace ronk;
+
+extern "C" size_t ronk_sort_rows_workspace_bytes(int S, int N) {
+    if (S < 1 || N < 1) return 0;
+    const long long n = (long long)S * N;
+    const int nblocks = (int)((n + kSortTile - 1) / kSortTile);
+    return 2 * align256((size_t)n * 8) + align256((size_t)256 * nblocks * 4);
+}
+
+extern "C" int ronk_sort_rows(const float* scores, const float* boxes, int S, int N, int K, float* out_scores,
+                              float* out_boxes, int32_t* out_idx, void* ws, size_t ws_bytes, void* stream) {
+    RONK_REQUIRE(scores && out_scores && ws, RONK_EINVAL, "ronk_sort_rows: NULL argument");
+    RONK_REQUIRE((boxes == nullptr) == (out_boxes == nullptr), RONK_EINVAL, "ronk_sort_rows: boxes and out_boxes go together");
+    RONK_REQUIRE(S >= 1 && S <= 256 && N >= 1 && N < (1 << 24) && K >= 1 && K <= N, RONK_EINVAL,
+                 "ronk_sort_rows: 1 <= S <= 256, 1 <= K <= N < 2^24");
+    RONK_REQUIRE(!boxes || (((uintptr_t)boxes % 16) == 0 && ((uintptr_t)out_boxes % 16) == 0), RONK_EINVAL,
+                 "ronk_sort_rows: box pointers must be 16-byte aligned");
+    const long long n = (long long)S * N;
+    RONK_REQUIRE(n < (1ll << 31) - kSortTile, RONK_ELIMIT, "ronk_sort_rows: too many elements");
+    RONK_REQUIRE(ws_bytes >= ronk_sort_rows_workspace_bytes(S, N), RONK_EINVAL, "ronk_sort_rows: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblocks = (int)((n + kSortTile - 1) / kSortTile);
+    unsigned char* w = (unsigned char*)ws;
+    u64* buf[2] = {(u64*)w, (u64*)(w + align256((size_t)n * 8))};
+    unsigned* hist = (unsigned*)(w + 2 * align256((size_t)n * 8));
+    rows_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scores, N, n, buf[0]);
+    RONK_LAUNCHED();
+    int cur = 0;
+    for (int byte = 0; byte < 8; ++byte) {
+        // bytes 0..2: column (those above the width of N - 1 are zero), 3..6: score, 7: row
+        if (byte < 3 && ((unsigned)(N - 1) >> (8 * byte)) == 0u) continue;
+        if (byte == 7 && S == 1) continue;
+        if (int rc = radix_pass(buf[cur], buf[cur ^ 1], n, 8 + byte, hist, nblocks, st)) return rc;
+        cur ^= 1;
+    }
+    const long long total = (long long)S * K;
+    rows_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(buf[cur], scores, (const float4*)boxes, N, K, total,
+                                                                        out_scores, (float4*)out_boxes, out_idx);
+    RONK_LAUNCHED();
+    return RONK_OK;
+}
 
 extern "C" size_t ronk_average_precision_workspace_bytes(long long n, int C) {
     if (n < 0 || C < 2) return 0;
@@ -489,12 +573,7 @@ extern "C" int ronk_average_precision_records(const uint64_t* records, long long
     int cur = 0;
     if (n > 0) {
         for (int pass = 0; pass < 4 + class_passes; ++pass) {
-            ap_sort_hist_kernel<<<L.nblocks, kSortThreads, 0, st>>>(src, n, pass, hist, L.nblocks);
-            RONK_LAUNCHED();
-            ap_scan_u32_kernel<<<1, 1024, 0, st>>>(hist, 256 * L.nblocks);
-            RONK_LAUNCHED();
-            ap_sort_scatter_kernel<<<L.nblocks, kSortThreads, 0, st>>>(src, buf[cur], n, pass, hist, L.nblocks);
-            RONK_LAUNCHED();
+            if (int rc = radix_pass(src, buf[cur], n, pass, hist, L.nblocks, st)) return rc;
             src = buf[cur];
             cur ^= 1;
         }

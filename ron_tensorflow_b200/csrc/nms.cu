@@ -603,7 +603,7 @@ nms_staged_kernel(const __grid_constant__ NmsParams p) {
 struct RowSrc {
     const float* g;
     __device__ __forceinline__ u64 get(int i) const {
-        unsigned u = __float_as_uint(g[i]);
+        unsigned u = __float_as_uint(g[i] + 0.f);          // -0 -> +0: the two zeros tie (lower index first)
         u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
         return ((u64)u << 32) | (u64)(0xffffffffu - (unsigned)i);
     }

@@ -1034,11 +1034,8 @@ clip_kernel(const float4* __restrict__ in, long long n, float4 ref, float4* __re
 
 // ------------------------------------------------------------------ generic bboxes_sort
 __device__ __forceinline__ unsigned orderable(float s) {
-    unsigned u = __float_as_uint(s);
+    unsigned u = __float_as_uint(s + 0.f);          // -0 -> +0: tf.nn.top_k compares values, the two zeros tie
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unorderable(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
 struct ScoreSrc {
@@ -1064,8 +1061,8 @@ sort_topk_kernel(const float* __restrict__ scores, const float4* __restrict__ bo
         float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
         int idx = -1;
         if (k != 0ull) {
-            sc = unorderable((unsigned)(k >> 32));
             idx = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
+            sc = scores[row * N + idx];
             box = boxes[row * N + idx];
         }
         out_scores[row * K + r] = sc;

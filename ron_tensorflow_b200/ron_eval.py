@@ -51,15 +51,14 @@ def filter_boxes(scores, labels, bboxes, min_size_ratio, image_shape, net_input_
             core.gather_rows(core.as_cuda(labels, torch.int64, b.device), idx), core.gather_rows(b, idx))
 
 
-MAX_SORT = 16384          # ronk_sort_topk: the winners are sorted in shared memory
+MAX_SORT = 1 << 24        # core.sort_topk: shared-memory sort up to 16 384 boxes, global-memory radix sort (ronk_sort_rows) above
 MAX_KEEP = 2048           # ronk_nms_batch: the kept list lives in shared memory
 
 
 def _check_limits(n, keep_top_k, what):
     """The reference's tf.nn.top_k(k = number of boxes) has no upper bound; the kernels behind these functions do."""
-    if n > MAX_SORT:
-        raise ValueError('%s: %d boxes pass FLAGS.select_threshold / objectness_thres, the sort kernel takes at most %d '
-                         '(raise the thresholds, or use the fused RONNet.detect path, which selects per class)' % (what, n, MAX_SORT))
+    if n >= MAX_SORT:
+        raise ValueError('%s: %d boxes pass FLAGS.select_threshold / objectness_thres, the sort takes fewer than %d' % (what, n, MAX_SORT))
     if keep_top_k > MAX_KEEP:
         raise ValueError('%s: keep_top_k = %d, the NMS kernel keeps at most %d boxes per row' % (what, keep_top_k, MAX_KEEP))
 

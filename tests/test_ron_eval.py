@@ -116,3 +116,58 @@ def test_cuda_vs_oracle_dense_and_empty():
         assert rs.shape == (0,) and rl.shape == (0,) and rb.shape == (0, 4)
     rs, rl, rb = ron_eval.tf_bboxes_nms_by_class(s, l, b)      # n < 1: the inputs come back unchanged (:291)
     assert rs.shape == (0, 21) and rl.shape == (0,) and rb.shape == (0, 4)
+
+
+@pytest.mark.gpu
+def test_more_boxes_than_the_shared_memory_sort_takes():
+    """The reference sorts with tf.nn.top_k(k = number of boxes) (ron_eval.py:155 / :217 / :301), which has no bound;
+    beyond 16 384 boxes the CUDA path switches to the global-memory radix sort (ronk_sort_rows).  (a) core.sort_topk
+    on rows of 40 000 scores with heavy ties, negative values and +-0 against the oracle's stable top-k; (b) the three
+    NMS variants on all ~21 000 RON-320 boxes of one image (thresholds low enough that nearly every box passes) against
+    the oracle; (c) core.nms_batch on unsorted rows longer than 16 384."""
+    need_cuda()
+    import torch
+    from ron_tensorflow_b200 import core, ron_eval
+    rng = np.random.Generator(np.random.PCG64(77))
+    S, N = 3, 40000
+    sc = rng.normal(0., 1., size=(S, N)).astype(np.float32)
+    sc[0] = np.round(sc[0], 1)                                       # ~60 distinct values: long tie runs
+    sc[1, ::7] = 0.
+    sc[1, 3::11] = -0.
+    bx = rng.uniform(0, 1, size=(S, N, 4)).astype(np.float32)
+    for K in (N, 20000):
+        ss, sb, si = core.sort_topk(torch.from_numpy(sc), torch.from_numpy(bx), K, want_idx=True)
+        for r in range(S):
+            o = O.topk_stable(sc[r], K)
+            eq(si[r], o.astype(np.int32), 'order of row %d' % r)
+            eq(ss[r], sc[r][o], 'scores'); eq(sb[r], bx[r][o], 'boxes')
+    # (c) unsorted NMS rows
+    b2 = np.concatenate([bx[:1, :, :2] * 0.9, bx[:1, :, :2] * 0.9 + 0.02 + 0.08 * bx[:1, :, 2:]], -1).astype(np.float32)
+    s2 = np.abs(sc[2:3]) + np.float32(0.01)
+    ns, nb, ni = core.nms_batch(torch.from_numpy(s2), torch.from_numpy(b2), 0.3, 150, 'min', assume_sorted=False, want_idx=True)
+    o_s, o_b, o_i = O.nms(s2[0], b2[0], 0.3, 150, 'min')
+    eq(ni[0], o_i.astype(np.int32), 'kept indices'); eq(ns[0], o_s, 'kept scores'); eq(nb[0], o_b, 'kept boxes')
+    # (b) ron_eval on (nearly) every box of an image
+    dec = O.flat_decode_anchors(O.anchors_all_layers(O.RON320))
+    loc, pred, obj = synth.make_predictions(405, 1, 21250, 21, hot=300, dense=True)
+    obj = np.maximum(obj, np.float32(0.5))
+    boxes = O.decode(loc[0], dec)
+    P = synth.split_layers(pred, LS); Ob = synth.split_layers(obj[..., None], LS); Bx = synth.split_layers(boxes[None], LS)
+    old = ron_eval.FLAGS.select_threshold, ron_eval.FLAGS.objectness_thres
+    try:
+        ron_eval.FLAGS.select_threshold, ron_eval.FLAGS.objectness_thres = 1e-5, 0.03
+        s, l, b = ron_eval.flaten_predict(P, Ob, [torch.from_numpy(t) for t in Bx])
+        os_, ol, ob = O.flaten_predict([pred[0]], [obj[0]], [boxes], 0.03)
+        assert os_.shape[0] > 16384
+        eq(s, os_, 'scores')
+        cs, cl, cb = ron_eval.tf_bboxes_nms_by_class(s, l, b, nms_threshold=0.45, keep_top_k=30, mode='min')
+        rs, rl, rb = O.bboxes_nms_by_class(os_, ol, ob, 1e-5, 0.45, 30, 'min')
+        eq(cs, rs, 'by-class scores'); eq(cl, rl, 'by-class labels'); eq(cb, rb, 'by-class boxes')
+        cs, cl, cb = ron_eval.tf_bboxes_nms_by_class_v1(s, l, b, nms_threshold=0.45, keep_top_k=30, mode='min')
+        rs, rl, rb = O.bboxes_nms_by_class_v1(os_, ol, ob, 1e-5, 21, 0.45, 30, 'min')
+        eq(cs, rs, 'v1 scores'); eq(cl, rl, 'v1 labels'); eq(cb, rb, 'v1 boxes')
+        cs, cl, cb = ron_eval.tf_bboxes_nms(s, l, b, nms_threshold=0.45, keep_top_k=100, mode='union')
+        rs, rl, rb = O.bboxes_nms_agnostic(os_, ol, ob, 1e-5, 0.45, 100, 'union')
+        eq(cs, rs, 'nms scores'); eq(cl, rl, 'nms labels'); eq(cb, rb, 'nms boxes')
+    finally:
+        ron_eval.FLAGS.select_threshold, ron_eval.FLAGS.objectness_thres = old
