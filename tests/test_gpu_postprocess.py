@@ -247,7 +247,7 @@ def test_fine_grained_functions(golden):
 
 
 @pytest.mark.parametrize('path', ['sampled', 'unsampled', 'rebuild'])
-@pytest.mark.parametrize('dense,K', [(False, 400), (True, 400), (False, 64), (True, 1500)])
+@pytest.mark.parametrize('dense,K', [(False, 400), (True, 400), (False, 64), (True, 1500), (False, 1500), (True, 5000)])
 def test_topk_paths_vs_oracle(ron, dec_anchors, path, dense, K):
     """The three ways the top-k kernel can arrive at its list -- sampled pivot + second scatter
     launch, one plain scatter launch, and the exact rebuild after a (forced) too-high pivot --
