@@ -834,30 +834,11 @@ __device__ u64 large_kth(const u64* g, int n, int K, unsigned* s_hist, int* s_ct
     return prefix;
 }
 
-// a[0..m) -> sorted descending (result pointer returned: a or b), stable LSD radix sort on the bytes that differ.
+// stable LSD radix sort (descending) of a[0..m) on the bytes that are non-zero in `diff`; result pointer returned (a or b).
 // The histogram of a pass is accumulated while the previous pass scatters (plain shared-memory atomics).
-__device__ u64* large_sort_desc(u64* a, u64* b, int m, unsigned* s_total, unsigned* s_base, unsigned short* s_wcnt,
-                                int* s_ctl) {
+__device__ u64* large_sort_bytes(u64* a, u64* b, int m, u64 diff, unsigned* s_total, unsigned* s_base, unsigned short* s_wcnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
-    // bytes that are the same in every key need no pass: OR / AND of all keys
-    unsigned* s_red = reinterpret_cast<unsigned*>(s_ctl);       // or_lo, or_hi, and_lo, and_hi
-    if (tid == 0) { s_red[0] = 0u; s_red[1] = 0u; s_red[2] = 0xffffffffu; s_red[3] = 0xffffffffu; }
-    __syncthreads();
-    {
-        unsigned ol = 0u, oh = 0u, al = 0xffffffffu, ah = 0xffffffffu;
-        for (int i = tid; i < m; i += kLargeThreads) {
-            const u64 k = a[i];
-            ol |= (unsigned)k; oh |= (unsigned)(k >> 32);
-            al &= (unsigned)k; ah &= (unsigned)(k >> 32);
-        }
-        ol = __reduce_or_sync(full, ol); oh = __reduce_or_sync(full, oh);
-        al = __reduce_and_sync(full, al); ah = __reduce_and_sync(full, ah);
-        if (lane == 0) { atomicOr(&s_red[0], ol); atomicOr(&s_red[1], oh); atomicAnd(&s_red[2], al); atomicAnd(&s_red[3], ah); }
-    }
-    __syncthreads();
-    const u64 diff = (((u64)s_red[1] << 32) | s_red[0]) ^ (((u64)s_red[3] << 32) | s_red[2]);
-    __syncthreads();
     if (m < 2 || diff == 0ull) return a;
     int byte = 0;
     while (((diff >> (8 * byte)) & 255ull) == 0ull) ++byte;
@@ -926,6 +907,71 @@ __device__ u64* large_sort_desc(u64* a, u64* b, int m, unsigned* s_total, unsign
         byte = next;
     }
     return a;
+}
+
+// a[0..m) -> sorted descending (result pointer returned: a or b).  Bytes that are equal in every key (OR / AND of all
+// keys) get no pass.  Scores rarely tie, so the low word (~anchor, 2 varying bytes) is left out at first: four passes over
+// the score bytes, then a scan for runs of equal scores -- short runs (<= 16 keys) are put in order by the thread at their
+// head, a longer run sends the segment through the full sort.
+__device__ u64* large_sort_desc(u64* a, u64* b, int m, unsigned* s_total, unsigned* s_base, unsigned short* s_wcnt,
+                                int* s_ctl) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned full = 0xffffffffu;
+    // bytes that are the same in every key need no pass: OR / AND of all keys
+    unsigned* s_red = reinterpret_cast<unsigned*>(s_ctl);       // or_lo, or_hi, and_lo, and_hi
+    if (tid == 0) { s_red[0] = 0u; s_red[1] = 0u; s_red[2] = 0xffffffffu; s_red[3] = 0xffffffffu; }
+    __syncthreads();
+    {
+        unsigned ol = 0u, oh = 0u, al = 0xffffffffu, ah = 0xffffffffu;
+        for (int i = tid; i < m; i += kLargeThreads) {
+            const u64 k = a[i];
+            ol |= (unsigned)k; oh |= (unsigned)(k >> 32);
+            al &= (unsigned)k; ah &= (unsigned)(k >> 32);
+        }
+        ol = __reduce_or_sync(full, ol); oh = __reduce_or_sync(full, oh);
+        al = __reduce_and_sync(full, al); ah = __reduce_and_sync(full, ah);
+        if (lane == 0) { atomicOr(&s_red[0], ol); atomicOr(&s_red[1], oh); atomicAnd(&s_red[2], al); atomicAnd(&s_red[3], ah); }
+    }
+    __syncthreads();
+    const u64 diff = (((u64)s_red[1] << 32) | s_red[0]) ^ (((u64)s_red[3] << 32) | s_red[2]);
+    __syncthreads();
+    if (m < 2 || diff == 0ull) return a;
+    const u64 hi = diff & 0xffffffff00000000ull;
+    if (hi == 0ull || (diff & 0xffffffffull) == 0ull) return large_sort_bytes(a, b, m, diff, s_total, s_base, s_wcnt);
+    u64* r = large_sort_bytes(a, b, m, hi, s_total, s_base, s_wcnt);
+    u64* other = (r == a) ? b : a;
+    // runs of equal scores: heads found read-only, then (barrier) put in order
+    if (tid == 0) s_ctl[0] = 0;
+    __syncthreads();
+    bool longrun = false;
+    for (int i = tid; i < m - 1; i += kLargeThreads) {
+        const unsigned sc = (unsigned)(r[i] >> 32);
+        if ((unsigned)(r[i + 1] >> 32) == sc && (i == 0 || (unsigned)(r[i - 1] >> 32) != sc)) {
+            int L = 2;
+            while (i + L < m && L <= 16 && (unsigned)(r[i + L] >> 32) == sc) ++L;
+            if (L > 16) longrun = true;
+        }
+    }
+    if (longrun) s_ctl[0] = 1;
+    __syncthreads();
+    const bool redo = s_ctl[0] != 0;
+    __syncthreads();
+    if (redo) return large_sort_bytes(r, other, m, diff, s_total, s_base, s_wcnt);
+    for (int i = tid; i < m - 1; i += kLargeThreads) {
+        const unsigned sc = (unsigned)(r[i] >> 32);
+        if ((unsigned)(r[i + 1] >> 32) == sc && (i == 0 || (unsigned)(r[i - 1] >> 32) != sc)) {
+            int L = 2;
+            while (i + L < m && (unsigned)(r[i + L] >> 32) == sc) ++L;          // <= 16 here
+            for (int x = 1; x < L; ++x) {                                        // insertion sort, descending keys
+                const u64 k = r[i + x];
+                int y = x - 1;
+                while (y >= 0 && r[i + y] < k) { r[i + y + 1] = r[i + y]; --y; }
+                r[i + y + 1] = k;
+            }
+        }
+    }
+    __syncthreads();
+    return r;
 }
 
 __global__ void __launch_bounds__(kLargeThreads, 1)

@@ -268,6 +268,31 @@ def test_topk_paths_vs_oracle(ron, dec_anchors, path, dense, K):
         eq(bx[b], ob, 'boxes b=%d' % b)
 
 
+@pytest.mark.parametrize('decimals', [2, 4])
+def test_large_topk_with_score_ties(ron, dec_anchors, decimals):
+    """top_k in the thousands with tied scores (the radix-sort select kernel sorts by the score bytes first and repairs
+    runs of equal scores afterwards): scores rounded to 4 decimals give many short runs (ordered in place by the run's
+    head thread), to 2 decimals runs of hundreds (the segment falls back to the full sort).  Order among equal scores =
+    lower anchor first, like tf.nn.top_k."""
+    from ron_tensorflow_b200 import core
+    net, anchors = ron
+    B, K = 2, 3000
+    loc, pred, obj = synth.make_predictions(900 + decimals, B, 21250, 21, hot=300, dense=True)
+    pred = np.round(pred, decimals).astype(np.float32)
+    s, bx, ix = core.decode_select_topk(anchors.anchor_set, _layers(loc, False), _layers(pred, False), _layers(obj, False),
+                                        0.03, 0.01, [0., 0., 1., 1.], 0.03, K, want_idx=True)
+    ties = 0
+    for b in range(B):
+        boxes = O.decode(loc[b], dec_anchors)
+        gate = (obj[b] > np.float32(0.03)).astype(np.float32)
+        os_, ob, oi = O.select_topk_image(gate[:, None] * pred[b], boxes, 0.01, K, [0., 0., 1., 1.], 0.03)
+        ties += int((np.diff(os_, axis=-1) == 0).sum())
+        eq(ix[b], oi, 'anchor idx b=%d' % b)
+        eq(s[b], os_, 'scores b=%d' % b)
+        eq(bx[b], ob, 'boxes b=%d' % b)
+    assert ties > 1000
+
+
 def test_ssd512_postprocess_vs_oracle():
     """BASELINE config 4 shape on the post-process side: SSD-512 anchors (24 564, 7 layers, tiles
     that end mid-row), SSD order (no objectness gate, no clip, no min-size)."""
