@@ -599,13 +599,14 @@ pivot_kernel(const __grid_constant__ PostParams p) {
 // Exact rebuild of one (image, class) list straight from the inputs (the sampled pivot turned out
 // too high, probability ~1e-4 per segment): objectness gate, box validity from the box table's NaN
 // marker, score > sel_thr.  Returns the new length (block-uniform).
+template <int NT>
 __device__ int rebuild_list(const PostParams& p, int b, int c, u64* g, int* s_cnt) {
     const int tid = threadIdx.x;
     if (tid == 0) *s_cnt = 0;
     __syncthreads();
     for (int l = 0; l < p.tab.L; ++l) {
         const int n_l = p.tab.offs[l + 1] - p.tab.offs[l];
-        for (int i0 = 0; i0 < n_l; i0 += (int)blockDim.x) {
+        for (int i0 = 0; i0 < n_l; i0 += NT) {
             const int i = i0 + tid;
             bool sel = false;
             float v = 0.f;
@@ -729,7 +730,7 @@ select_topk_kernel(const __grid_constant__ PostParams p) {
     const u64 kth = s_sort[p.K - 1];
     if ((kth >> 32) != 0ull && __uint_as_float((unsigned)(kth >> 32)) > seg_thr && !p.force_rebuild) break;
     __syncthreads();
-    n = rebuild_list(p, b, seg - b * CM + 1, g, &s_cnt);
+    n = rebuild_list<kTopkThreads>(p, b, seg - b * CM + 1, g, &s_cnt);
     n = n > p.cap ? p.cap : n;
     }
     for (int r = tid; r < p.K; r += kTopkThreads) {
@@ -1034,7 +1035,7 @@ select_topk_large_kernel(const __grid_constant__ PostParams p) {
         if (attempt > 0 || !(seg_thr > p.sel_thr)) break;
         if (m >= p.K && __uint_as_float((unsigned)(sorted[p.K - 1] >> 32)) > seg_thr && !p.force_rebuild) break;
         __syncthreads();
-        n = rebuild_list(p, b, seg - b * CM + 1, g, &s_cnt);
+        n = rebuild_list<kLargeThreads>(p, b, seg - b * CM + 1, g, &s_cnt);
         n = n > p.cap ? p.cap : n;
     }
     for (int r = tid; r < p.K; r += kLargeThreads) {
