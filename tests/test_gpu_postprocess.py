@@ -131,7 +131,21 @@ def test_bboxes_nms_golden(golden, mode, thr, M):
     eq(b, g['%s_%g_%d_boxes' % (mode, thr, M)], 'boxes')
 
 
-def test_nms_batch_sort_clip_golden(golden):
+@pytest.fixture(params=['auto', 'warp', 'wide', 'staged'])
+def nms_variant(request, monkeypatch):
+    """Every NMS kernel on every NMS case: the dispatch's own choice, one warp per segment (nms_kernel), a CTA per
+    segment (nms_wide_kernel), and the two-stage CTA kernel for long lists (nms_staged_kernel; rows keeping <= 32 boxes
+    fall back inside the library)."""
+    env = {'auto': {}, 'warp': {'RONK_NMS_STAGED': '0', 'RONK_NMS_WIDE': '0'}, 'wide': {'RONK_NMS_STAGED': '0', 'RONK_NMS_WIDE': '4'},
+           'staged': {'RONK_NMS_STAGED': '1'}}[request.param]
+    for k in ('RONK_NMS_STAGED', 'RONK_NMS_WIDE'):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    return request.param
+
+
+def test_nms_batch_sort_clip_golden(golden, nms_variant):
     need_cuda()
     import ron_tensorflow_b200.tf_extended as tfe
     g = golden('nms')
@@ -155,7 +169,7 @@ def test_nms_batch_sort_clip_golden(golden):
 
 @pytest.mark.parametrize('K,M,mode', [(400, 200, 'min'), (400, 200, 'union'), (1000, 50, 'min'), (33, 40, 'min'),
                                       (2500, 300, 'union')])
-def test_nms_random_vs_oracle(K, M, mode):
+def test_nms_random_vs_oracle(K, M, mode, nms_variant):
     need_cuda()
     from ron_tensorflow_b200 import core
     rng = np.random.Generator(np.random.PCG64(K * 7 + M))
@@ -173,6 +187,37 @@ def test_nms_random_vs_oracle(K, M, mode):
     eq(ix, oi, 'kept positions')
     eq(s, os_, 'scores')
     eq(b, ob, 'boxes')
+
+
+@pytest.mark.parametrize('case', ['outside_unit', 'zero_threshold', 'long_crowded', 'empty_boxes'])
+def test_nms_special_cases_vs_oracle(case, nms_variant):
+    """Cases that leave the fast path of the NMS kernels: coordinates outside [0, 1] (no saturating clamps), a threshold
+    of 0 (a zero overlap suppresses), a long crowded list (6 000 candidates, most of them suppressed: the staged kernel's
+    prefix filter and queue), boxes of zero area among the candidates."""
+    need_cuda()
+    from ron_tensorflow_b200 import core
+    rng = np.random.Generator(np.random.PCG64({'outside_unit': 1, 'zero_threshold': 2, 'long_crowded': 3, 'empty_boxes': 4}[case]))
+    S, K, M, thr, mode = 5, 700, 120, 0.45, 'min'
+    if case == 'long_crowded':
+        S, K, M = 3, 6000, 200
+    c = rng.uniform(0.1, 0.9, size=(S, K, 2))
+    sz = np.exp(rng.uniform(np.log(0.02), np.log(0.5), size=(S, K, 2)))
+    boxes = np.concatenate([c - sz / 2, c + sz / 2], -1).astype(np.float32)
+    scores = np.sort(rng.uniform(0.01, 1, size=(S, K)).astype(np.float32), axis=-1)[:, ::-1].copy()
+    if case == 'outside_unit':
+        boxes = boxes * np.float32(3.) - np.float32(0.7)
+        mode = 'union'
+        boxes[1] = (boxes[1] + np.float32(0.7)) / np.float32(3.)          # one row inside the unit square, 'union'
+    if case == 'zero_threshold':
+        thr = 0.
+    if case == 'empty_boxes':
+        boxes[:, ::5, 2] = boxes[:, ::5, 0]                               # zero height
+        boxes[:, 3::11, 3] = boxes[:, 3::11, 1] - np.float32(0.01)        # negative width
+    for sorted_ in (True, False):
+        sc = scores if sorted_ else scores[:, rng.permutation(K)]
+        s, b, ix = core.nms_batch(sc, boxes, thr, M, mode, assume_sorted=sorted_, want_idx=True)
+        os_, ob, oi = O.nms_batch(sc, boxes, thr, M, mode)
+        eq(ix, oi, 'kept positions'); eq(s, os_, 'scores'); eq(b, ob, 'boxes')
 
 
 def test_tpfp_golden_and_random(golden):
