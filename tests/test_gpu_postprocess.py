@@ -503,7 +503,7 @@ def _oracle_ap(cls, scores, tp, fp, n_gt, C):
     return out
 
 
-@pytest.mark.parametrize('case', ['random', 'ties', 'large', 'sparse_classes', 'many_classes'])
+@pytest.mark.parametrize('case', ['random', 'ties', 'large', 'sparse_classes', 'many_classes', 'exact_tiles', 'one_record'])
 def test_average_precision_records_vs_oracle(case):
     """tfe.average_precision_records (device: stable radix sort + per-class float64 curves) against the oracle's
     precision_recall / average_precision_voc07 / _voc12 (tf_extended/metrics.py:100-130, :212-258) class by class:
@@ -514,9 +514,13 @@ def test_average_precision_records_vs_oracle(case):
     need_cuda()
     import torch
     import ron_tensorflow_b200.tf_extended as tfe
-    rng = np.random.Generator(np.random.PCG64({'random': 1, 'ties': 2, 'large': 3, 'sparse_classes': 4, 'many_classes': 5}[case]))
-    C, n = {'random': (21, 5000), 'ties': (5, 6000), 'large': (4, 200000), 'sparse_classes': (12, 3000), 'many_classes': (301, 20000)}[case]
+    rng = np.random.Generator(np.random.PCG64({'random': 1, 'ties': 2, 'large': 3, 'sparse_classes': 4, 'many_classes': 5,
+                                               'exact_tiles': 6, 'one_record': 7}[case]))
+    C, n = {'random': (21, 5000), 'ties': (5, 6000), 'large': (4, 200000), 'sparse_classes': (12, 3000), 'many_classes': (301, 20000),
+            'exact_tiles': (4, 16384 - 42), 'one_record': (3, 1)}[case]
     cls = rng.integers(0, C - 1, size=n)
+    if case == 'exact_tiles':          # class sizes 4096 / 2048 / rest: boundaries on AP tiles; 16 384 entries with the padding: two full sort tiles
+        cls = np.concatenate([np.zeros(4096, np.int64), np.ones(2048, np.int64), np.full(n - 6144, 2, np.int64)])[rng.permutation(n)]
     if case == 'sparse_classes':
         cls = rng.choice(np.array([0, 3, 4, 10]), size=n)                      # classes 2, 3, 6.. have no record at all
     scores = rng.uniform(1.1e-4, 1., size=n).astype(np.float32)
