@@ -625,7 +625,9 @@ __device__ int rebuild_list(const PostParams& p, int b, int c, u64* g, int* s_cn
         }
     }
     __syncthreads();
-    return *s_cnt;
+    const int n = *s_cnt;
+    __syncthreads();          // every thread has its copy before the caller reuses the counter
+    return n;
 }
 
 // One CTA per (image, class): exact top-K of the candidate list, sorted descending
