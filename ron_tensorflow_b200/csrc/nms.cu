@@ -72,9 +72,10 @@ nms_kernel(const __grid_constant__ NmsParams p) {
     unsigned char* base = smem + (size_t)warp * per_warp;
     float4* s_kbox = reinterpret_cast<float4*>(base);
     float4* s_cbox = s_kbox + p.M + kNmsPad;
-    float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
-    float* s_cvol = s_kvol + p.M;
-    float* s_kt = s_cvol + 32;            // thr * vol of the kept boxes (+inf for empty boxes: they suppress nothing)
+    // (s_kvol sits between s_cvol and s_kt: the compiler reads it four entries at a time, up to three past `count`)
+    float* s_cvol = reinterpret_cast<float*>(s_cbox + 32);
+    float* s_kvol = s_cvol + 32;
+    float* s_kt = s_kvol + p.M;           // thr * vol of the kept boxes (+inf for empty boxes: they suppress nothing)
     // Sentinels behind the kept list: a box no candidate intersects, with threshold +inf.  The fast loop below
     // then always runs whole groups of kNmsPad kept boxes, fully unrolled, without a bound inside the group.
     for (int i = lane; i < p.M + kNmsPad; i += 32) {
@@ -210,9 +211,9 @@ nms_wide_kernel(const __grid_constant__ NmsParams p) {
     if (p.only_flagged && !p.only_flagged[seg]) return;
     float4* s_kbox = reinterpret_cast<float4*>(smem);
     float4* s_cbox = s_kbox + p.M + kWidePad;
-    float* s_kvol = reinterpret_cast<float*>(s_cbox + 32);
-    float* s_cvol = s_kvol + p.M;
-    float* s_kt = s_cvol + 32;
+    float* s_cvol = reinterpret_cast<float*>(s_cbox + 32);
+    float* s_kvol = s_cvol + 32;
+    float* s_kt = s_kvol + p.M;
     for (int i = threadIdx.x; i < p.M + kWidePad; i += W * 32) {
         s_kbox[i] = make_float4(2.f, 2.f, -1.f, -1.f);
         s_kt[i] = __int_as_float(0x7f800000);
@@ -379,9 +380,9 @@ nms_staged_kernel(const __grid_constant__ NmsParams p) {
     float4* s_kbox = reinterpret_cast<float4*>(smem);
     float4* s_cbox = s_kbox + p.M + kWidePad;
     float4* q_box = s_cbox + 32;
-    float* s_kvol = reinterpret_cast<float*>(q_box + kStQ);
-    float* s_cvol = s_kvol + p.M;
-    float* s_kt = s_cvol + 32;
+    float* s_cvol = reinterpret_cast<float*>(q_box + kStQ);
+    float* s_kvol = s_cvol + 32;
+    float* s_kt = s_kvol + p.M;
     float* q_score = s_kt + p.M + kWidePad;
     int* q_pos = reinterpret_cast<int*>(q_score + kStQ);
     for (int i = threadIdx.x; i < p.M + kWidePad; i += W * 32) {

@@ -943,34 +943,36 @@ __device__ u64* large_sort_desc(u64* a, u64* b, int m, unsigned* s_total, unsign
     if (hi == 0ull || (diff & 0xffffffffull) == 0ull) return large_sort_bytes(a, b, m, diff, s_total, s_base, s_wcnt);
     u64* r = large_sort_bytes(a, b, m, hi, s_total, s_base, s_wcnt);
     u64* other = (r == a) ? b : a;
-    // runs of equal scores: heads found read-only, then (barrier) put in order
+    // runs of equal scores: the heads and their lengths are found read-only and noted in the free buffer, then
+    // (barrier) every head puts its own run in order -- no thread touches another run
+    unsigned* runlen = reinterpret_cast<unsigned*>(other);          // m entries fit: the buffer holds K >= m keys
     if (tid == 0) s_ctl[0] = 0;
     __syncthreads();
     bool longrun = false;
-    for (int i = tid; i < m - 1; i += kLargeThreads) {
-        const unsigned sc = (unsigned)(r[i] >> 32);
-        if ((unsigned)(r[i + 1] >> 32) == sc && (i == 0 || (unsigned)(r[i - 1] >> 32) != sc)) {
-            int L = 2;
-            while (i + L < m && L <= 16 && (unsigned)(r[i + L] >> 32) == sc) ++L;
-            if (L > 16) longrun = true;
+    for (int i = tid; i < m; i += kLargeThreads) {
+        unsigned L = 0u;
+        if (i + 1 < m) {
+            const unsigned sc = (unsigned)(r[i] >> 32);
+            if ((unsigned)(r[i + 1] >> 32) == sc && (i == 0 || (unsigned)(r[i - 1] >> 32) != sc)) {
+                L = 2u;
+                while (i + (int)L < m && L <= 16u && (unsigned)(r[i + L] >> 32) == sc) ++L;
+                if (L > 16u) longrun = true;
+            }
         }
+        runlen[i] = L;
     }
     if (longrun) s_ctl[0] = 1;
     __syncthreads();
     const bool redo = s_ctl[0] != 0;
     __syncthreads();
     if (redo) return large_sort_bytes(r, other, m, diff, s_total, s_base, s_wcnt);
-    for (int i = tid; i < m - 1; i += kLargeThreads) {
-        const unsigned sc = (unsigned)(r[i] >> 32);
-        if ((unsigned)(r[i + 1] >> 32) == sc && (i == 0 || (unsigned)(r[i - 1] >> 32) != sc)) {
-            int L = 2;
-            while (i + L < m && (unsigned)(r[i + L] >> 32) == sc) ++L;          // <= 16 here
-            for (int x = 1; x < L; ++x) {                                        // insertion sort, descending keys
-                const u64 k = r[i + x];
-                int y = x - 1;
-                while (y >= 0 && r[i + y] < k) { r[i + y + 1] = r[i + y]; --y; }
-                r[i + y + 1] = k;
-            }
+    for (int i = tid; i < m; i += kLargeThreads) {
+        const int L = (int)runlen[i];
+        for (int x = 1; x < L; ++x) {                                            // insertion sort, descending keys
+            const u64 k = r[i + x];
+            int y = x - 1;
+            while (y >= 0 && r[i + y] < k) { r[i + y + 1] = r[i + y]; --y; }
+            r[i + y + 1] = k;
         }
     }
     __syncthreads();
