@@ -1039,9 +1039,9 @@ class HostEncoder(object):
                      d_out=dict(labels=torch.empty((self.B, N), dtype=torch.int64, device=dev),
                                 loc=torch.empty((self.B, N, 4), dtype=torch.float32, device=dev),
                                 scores=torch.empty((self.B, N), dtype=torch.float32, device=dev)),
-                     d_packet=torch.empty((self.packet_bytes,), dtype=torch.uint8, device=dev),
+                     d_packet=torch.zeros((self.packet_bytes,), dtype=torch.uint8, device=dev),   # (fixed-size copy: keep the unused tail defined)
                      h_packet=[pinned(self.packet_bytes) for _ in range(2)],
-                     d_lpacket=torch.empty((self.lpacket_bytes,), dtype=torch.uint8, device=dev),
+                     d_lpacket=torch.zeros((self.lpacket_bytes,), dtype=torch.uint8, device=dev),
                      h_lpacket=[pinned(self.lpacket_bytes) for _ in range(2)],
                      h_out=dict(labels=torch.zeros((self.B, N), dtype=torch.int64).pin_memory(),
                                 loc=torch.zeros((self.B, N, 4), dtype=torch.float32).pin_memory(),
