@@ -435,7 +435,10 @@ extern "C" int ronk_match_encode(const ronk_anchors_t* h, const float* gt_boxes,
     // slowest CTA (a coarse-layer tile against 50 GT boxes): cut those (table 1) or everything
     // (table 2) into 4 GT parts.  Large batches keep whole items (table 0): least overhead.
     const long long sets = (long long)B * ((p.Nin + kEncSet - 1) / kEncSet), slots = (long long)h->num_sms * 40;
-    int table = sets < slots / 2 ? 2 : (sets < slots * 2 ? 1 : 0);   // measured crossovers: batch ~13 and ~55 for RON-320
+    // measured crossovers for RON-320 (tools/enc_table_sweep.py): batch ~13 and ~55 with up to 50 GT boxes per image; with
+    // 100-200 boxes per image the heavy items are 2-4 x longer and cutting everything pays up to batch ~27
+    const long long fine = Gmax >= 100 ? slots : slots / 2;
+    int table = sets < fine ? 2 : (sets < slots * 2 ? 1 : 0);
     if (const char* e = getenv("RONK_ENC_TABLE")) {            // tuning knob
         int v = atoi(e);
         if (v >= 0 && v <= 2) table = v;
