@@ -583,6 +583,18 @@ def run_ours(args):
         cls = list(range(1, N_CLASSES))
         one = tfe.TpFpDeviceState(N_CLASSES, capacity=POST_B * (N_CLASSES - 1) * POST_M)
         one.update(n_gt, tp, fp, res['s'])
+        one.average_precision()                              # untimed: allocations, NCCL channels for these shapes
+        torch.cuda.synchronize()
+        barrier()
+        g0 = time.perf_counter()
+        rec_one, ngt_one = tfe.gather_tp_fp_records(one)     # the records stay on the device
+        torch.cuda.synchronize()
+        gather_dev_one_ms = max_over_ranks(time.perf_counter() - g0) * 1e3
+        g0 = time.perf_counter()
+        r_one = tfe.average_precision_records(rec_one, ngt_one, N_CLASSES)
+        ap_one = r_one['ap07'].cpu().numpy()
+        ap_dev_one_ms = max_over_ranks(time.perf_counter() - g0) * 1e3
+        del rec_one, r_one
         barrier()
         g0 = time.perf_counter()
         merged = tfe.gather_tp_fp(one, N_CLASSES)
@@ -592,6 +604,8 @@ def run_ours(args):
         for c in cls:
             p_, r_ = tfe.precision_recall(*merged[c].value())
             aps.append(tfe.average_precision_voc07(p_, r_))
+        if any(ap_one[c - 1] != aps[c - 1] for c in cls):
+            raise RuntimeError('bench: device AP07 of the one-batch gather differs from the host computation')
         del one
 
         # ---- the evaluation loop as the reference runs it (eval_ron_network.py:223-324) at VOC07-test size: 4952 images
@@ -731,10 +745,15 @@ def run_ours(args):
                     'h2d_bytes_per_step': int(sum(t.numel() * 4 for t in h_loc + h_pred + h_obj)),
                     'd2h_bytes_per_step': int(h_s.numel() * 4 + h_b.numel() * 4)},
             'gpu_launches': post_launches,
-            'tpfp_gather': {'backend': 'nccl' if world > 1 else 'none', 'ms': gather_ms, 'mAP_voc07_synthetic': float(np.mean(aps)),
+            'tpfp_gather': {'backend': 'nccl' if world > 1 else 'none', 'ms': gather_dev_one_ms, 'ap_ms': ap_dev_one_ms,
+                            'host_path_ms': gather_ms, 'mAP_voc07_synthetic': float(np.mean(aps)),
                             'records': int(sum(merged[c].scores.shape[0] for c in cls)),
-                            'note': 'one batch per rank, records appended on the device (tfe.TpFpDeviceState), host clock around '
-                                    'tfe.gather_tp_fp incl. the copy of all records to the host'},
+                            'note': 'one batch per rank, records appended on the device (tfe.TpFpDeviceState).  ms: host clock '
+                                    '(max over ranks) around tfe.gather_tp_fp_records -- the NCCL all-gather of the packed records, '
+                                    'which stay on the device; ap_ms: tfe.average_precision_records (sort + AP07 / AP12 of all '
+                                    'classes on the device, 20 doubles read back; AP07 checked bit-equal to the host path); '
+                                    'host_path_ms: tfe.gather_tp_fp, which also copies every record to the host and cuts the '
+                                    'per-class arrays there'},
             'eval_loop': eval_loop,
             'reference_call_sequence': refseq,
         }
